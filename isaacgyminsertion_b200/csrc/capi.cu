@@ -1,0 +1,18 @@
+// Library-wide pieces of the C-ABI: version and the thread-local error string.
+#include <stdarg.h>
+#include <string.h>
+
+#include "igi_common.cuh"
+#include "../../include/igi_b200.h"
+
+static thread_local char g_err[512] = "";
+
+void igi_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int igi_version(void) { return IGI_B200_VERSION; }
+extern "C" const char* igi_last_error(void) { return g_err; }

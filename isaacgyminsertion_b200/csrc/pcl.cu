@@ -1,0 +1,393 @@
+// (P) external-camera point-cloud path: K4 unproject/filter/compact, K5A gather, K5B FPS.
+// Entry points are declared in include/igi_b200.h.
+#include "igi_common.cuh"
+#include "../../include/igi_b200.h"
+
+namespace {
+
+constexpr int kCompactBlock = 256;
+constexpr int kMaxClasses = 4;
+
+struct CompactParams {
+  const float* depth;
+  const int32_t* seg;
+  const float* uvx;
+  const float* uvy;
+  const float* uvz;
+  const float* ext;
+  const float* e2g_inv;
+  float* out_pts;
+  int32_t* out_count;
+  int32_t* out_any;
+  int n_envs, H, W, n_classes;
+  int seg_ids[kMaxClasses];
+  float depth_max;  // < 0: disabled
+  int has_box;
+  float box[6];
+  int use_bulk;  // 1: TMA bulk copy of the env's depth/seg rows into smem
+};
+
+// One CTA per env.  The env's depth and segmentation rows (H*W*4 B each, 20 736 B
+// for 54x96) are staged into shared memory with two 1-D bulk async copies (TMA
+// engine) that complete on an mbarrier; every class (plug, socket) is then
+// produced from the staged tile, so HBM sees each input byte once.
+// Compaction keeps row-major pixel order (pcl_utils.py:71-72 boolean indexing):
+// each thread owns a contiguous pixel chunk, a block-wide exclusive scan of the
+// per-thread keep counts gives the output slot.
+__global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int npix = p.H * p.W;
+  float* s_depth = reinterpret_cast<float*>(smem_raw);
+  int32_t* s_seg = reinterpret_cast<int32_t*>(smem_raw + (size_t)npix * 4);
+  __shared__ uint64_t s_bar;
+  __shared__ int s_warp_tot[kCompactBlock / 32];
+  __shared__ int s_warp_any[kCompactBlock / 32];
+  __shared__ float s_m[32];  // ext (16) + e2g_inv (16)
+
+  const int env = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* g_depth = p.depth + (size_t)env * npix;
+  const int32_t* g_seg = p.seg ? p.seg + (size_t)env * npix : nullptr;
+
+  if (p.use_bulk) {
+    if (tid == 0) {
+      igi_mbar_init(&s_bar, 1);
+      igi_fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)npix * 4u;
+      igi_mbar_expect_tx(&s_bar, g_seg ? 2u * bytes : bytes);
+      igi_bulk_g2s(s_depth, g_depth, bytes, &s_bar);
+      if (g_seg) igi_bulk_g2s(s_seg, g_seg, bytes, &s_bar);
+    }
+  } else {
+    for (int i = tid; i < npix; i += kCompactBlock) {
+      s_depth[i] = g_depth[i];
+      if (g_seg) s_seg[i] = g_seg[i];
+    }
+  }
+  if (tid < 16) s_m[tid] = p.ext[(size_t)env * 16 + tid];
+  else if (tid < 32) s_m[tid] = p.e2g_inv[(size_t)env * 16 + (tid - 16)];
+  if (p.use_bulk) igi_mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  const float* uvx = p.uvx + (size_t)env * p.W;
+  const float* uvy = p.uvy + (size_t)env * p.H;
+  const float uvz = p.uvz[env];
+  const float* A = s_m;       // row-vector: w = [px,py,pz,1] @ A
+  const float* B = s_m + 16;  // o = w @ B^T
+
+  const int chunk = (npix + kCompactBlock - 1) / kCompactBlock;
+  const int lo = min(tid * chunk, npix);
+  const int hi = min(lo + chunk, npix);
+  const int lane = tid & 31, warp = tid >> 5;
+
+  for (int c = 0; c < p.n_classes; ++c) {
+    const int sid = p.seg_ids[c];
+    // pass 1: count kept pixels of this thread's chunk; pass 2: write them.
+    int kept = 0;
+    int any = 0;
+    float* out = p.out_pts + ((size_t)env * p.n_classes + c) * (size_t)npix * 3;
+    int base = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      int slot = base;
+      for (int i = lo; i < hi; ++i) {
+        float d = s_depth[i];
+        if (g_seg) d = __fmul_rn(d, (s_seg[i] == sid) ? 1.0f : 0.0f);  // -inf*0 = NaN, finite*0 = -0
+        bool ok = (p.depth_max < 0.0f) ? true : (d > -p.depth_max);
+        if (!ok) continue;
+        const int v = i / p.W, u = i - v * p.W;
+        const float px = __fmul_rn(uvx[u], d);
+        const float py = __fmul_rn(uvy[v], d);
+        const float pz = __fmul_rn(uvz, d);
+        // w = [px py pz 1] @ ext   (pcl_utils.py:77-83)
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          w[j] = fmaf(pz, A[8 + j], fmaf(py, A[4 + j], fmaf(px, A[j], A[12 + j])));
+        // o = w @ inverse(env_to_global)^T   (pcl_utils.py:84-85)
+        float o[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          o[j] = fmaf(w[3], B[4 * j + 3], fmaf(w[2], B[4 * j + 2], fmaf(w[1], B[4 * j + 1], w[0] * B[4 * j])));
+        if (p.has_box) {
+          ok = (o[0] >= p.box[0]) && (o[0] <= p.box[1]) && (o[1] >= p.box[2]) && (o[1] <= p.box[3]) &&
+               (o[2] >= p.box[4]) && (o[2] <= p.box[5]);
+          if (!ok) continue;
+        }
+        if (pass == 0) {
+          ++kept;
+          any |= (o[0] != 0.0f) | (o[1] != 0.0f) | (o[2] != 0.0f);
+        } else {
+          out[(size_t)slot * 3 + 0] = o[0];
+          out[(size_t)slot * 3 + 1] = o[1];
+          out[(size_t)slot * 3 + 2] = o[2];
+          ++slot;
+        }
+      }
+      if (pass == 0) {
+        // block-wide exclusive scan of `kept`
+        int incl = kept;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, incl, s);
+          if (lane >= s) incl += t;
+        }
+        const int wany = __any_sync(0xffffffffu, any);
+        __syncthreads();  // previous class finished reading s_warp_tot
+        if (lane == 31) s_warp_tot[warp] = incl;
+        if (lane == 0) s_warp_any[warp] = wany;
+        __syncthreads();
+        int woff = 0, total = 0, bany = 0;
+#pragma unroll
+        for (int wi = 0; wi < kCompactBlock / 32; ++wi) {
+          const int t = s_warp_tot[wi];
+          if (wi < warp) woff += t;
+          total += t;
+          bany |= s_warp_any[wi];
+        }
+        base = woff + incl - kept;
+        if (tid == 0) {
+          p.out_count[(size_t)env * p.n_classes + c] = total;
+          p.out_any[(size_t)env * p.n_classes + c] = bany;
+        }
+      }
+    }
+  }
+}
+
+// ---- K5A ---------------------------------------------------------------------
+// offsets[e] = m * #{e' < e : any[e']}; one CTA, block scan over envs.
+__global__ void __launch_bounds__(1024) pcl_offsets_kernel(const int32_t* any, int n_classes, int cls,
+                                                           int n_envs, int m, int32_t* offsets,
+                                                           int32_t* consumed) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_envs; base += 1024) {
+    const int e = base + tid;
+    const int f = (e < n_envs) ? (any[(size_t)e * n_classes + cls] != 0) : 0;
+    int incl = f;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int wi = 0; wi < 32; ++wi) {
+      const int t = s_w[wi];
+      if (wi < warp) woff += t;
+      tot += t;
+    }
+    const int carry = s_carry;
+    if (e < n_envs) offsets[e] = (carry + woff + incl - f) * m;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + tot;
+    __syncthreads();
+  }
+  if (tid == 0 && consumed) *consumed = s_carry * m;
+}
+
+__global__ void __launch_bounds__(128) pcl_gather_kernel(const float* pts, const int32_t* count,
+                                                         const int32_t* any, int n_classes, int cls, int cap,
+                                                         const uint32_t* raw, const int32_t* offsets, int m,
+                                                         float* out, int64_t out_stride, int32_t* out_idx) {
+  const int env = blockIdx.x;
+  const size_t t = (size_t)env * n_classes + cls;
+  const int n = count[t];
+  const bool live = any[t] != 0 && n > 0;
+  const float* src = pts + t * (size_t)cap * 3;
+  const uint32_t* r = raw + offsets[env];
+  float* dst = out + (size_t)env * out_stride;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    int id = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (live) {
+      id = (int)(r[i] % (uint32_t)n);  // ATen uniform_int_from_to: random() % range
+      x = src[(size_t)id * 3 + 0];
+      y = src[(size_t)id * 3 + 1];
+      z = src[(size_t)id * 3 + 2];
+    }
+    dst[(size_t)i * 3 + 0] = x;
+    dst[(size_t)i * 3 + 1] = y;
+    dst[(size_t)i * 3 + 2] = z;
+    if (out_idx) out_idx[(size_t)env * m + i] = id;
+  }
+}
+
+// ---- K5B FPS -------------------------------------------------------------------
+constexpr int kFpsBlock = 128;
+
+__device__ __forceinline__ uint32_t bitrev_n(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
+
+// Candidate ordering: larger distance wins; among equal distances the upstream
+// block reduction keeps the candidate of the thread whose id has the smaller
+// bit-reversed value, and inside a thread the smaller k (strict '>' while striding).
+// Packed so that a plain unsigned max picks the winner:
+//   hi = float_bits(d)+1 (0 = "no candidate" -> index 0), lo = ~tiekey.
+struct FpsCand {
+  uint32_t hi, lo;
+};
+
+__global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_t task_stride,
+                                                        const int32_t* count, const int32_t* any,
+                                                        int64_t count_stride, int n_fixed, int m,
+                                                        float* out_pts, int64_t out_stride, int32_t* out_idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int task = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = count ? count[(size_t)task * count_stride] : n_fixed;
+  const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
+  float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
+  int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
+  if (!live) {
+    for (int i = tid; i < m; i += kFpsBlock) {
+      if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
+      if (idst) idst[i] = 0;
+    }
+    return;
+  }
+  // smem: x[n] y[n] z[n] temp[n] (cap = n rounded up), then m selected ids
+  const int cap = (n + 3) & ~3;
+  float* sx = reinterpret_cast<float*>(smem_raw);
+  float* sy = sx + cap;
+  float* sz = sy + cap;
+  float* st = sz + cap;
+  __shared__ FpsCand s_cand[2][kFpsBlock / 32];
+
+  const float* src = pts + (size_t)task * task_stride;
+  for (int k = tid; k < n; k += kFpsBlock) {
+    sx[k] = src[(size_t)k * 3 + 0];
+    sy[k] = src[(size_t)k * 3 + 1];
+    sz[k] = src[(size_t)k * 3 + 2];
+    st[k] = 1e10f;
+  }
+  // upstream block size: largest power of two <= min(n, 512)
+  int lg = 31 - __clz(n);
+  if (lg > 9) lg = 9;
+  const uint32_t bmask = (1u << lg) - 1u;
+  __syncthreads();
+
+  int old = 0;
+  if (tid == 0) {
+    if (idst) idst[0] = 0;
+    if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
+  }
+  for (int j = 1; j < m; ++j) {
+    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    uint32_t bhi = 0, blo = 0;
+    for (int k = tid; k < n; k += kFpsBlock) {
+      const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
+      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+      if (mag <= 1e-3f) continue;
+      const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float d2 = fminf(d, st[k]);
+      st[k] = d2;
+      const uint32_t hi = __float_as_uint(d2) + 1u;
+      const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
+      const uint32_t lo = ~((rev << 16) | (uint32_t)k);
+      if (hi > bhi || (hi == bhi && lo > blo)) { bhi = hi; blo = lo; }
+    }
+    // warp arg-max with two REDUX passes
+    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
+    if (lane == 0) { s_cand[j & 1][warp].hi = whi; s_cand[j & 1][warp].lo = wlo; }
+    __syncthreads();
+    uint32_t fhi = 0, flo = 0;
+#pragma unroll
+    for (int wi = 0; wi < kFpsBlock / 32; ++wi) {
+      const FpsCand c = s_cand[j & 1][wi];
+      if (c.hi > fhi || (c.hi == fhi && c.lo > flo)) { fhi = c.hi; flo = c.lo; }
+    }
+    old = (fhi == 0) ? 0 : (int)((~flo) & 0xffffu);
+    if (tid == 0) {
+      if (idst) idst[j] = old;
+      if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int igi_pcl_compact(const float* depth, const int32_t* seg, const int32_t* seg_ids, int n_classes,
+                               const float* uvx, const float* uvy, const float* uvz, const float* ext,
+                               const float* e2g_inv, int n_envs, int H, int W, float depth_max,
+                               const float* box, float* out_pts, int32_t* out_count, int32_t* out_any,
+                               void* stream) {
+  IGI_REQUIRE(depth && uvx && uvy && uvz && ext && e2g_inv && out_pts && out_count && out_any,
+              "igi_pcl_compact: null pointer");
+  IGI_REQUIRE(n_envs >= 0 && H > 0 && W > 0, "igi_pcl_compact: bad dims");
+  IGI_REQUIRE(n_classes >= 1 && n_classes <= kMaxClasses, "igi_pcl_compact: n_classes must be 1..4");
+  IGI_REQUIRE(seg == nullptr || seg_ids != nullptr, "igi_pcl_compact: seg given without seg_ids");
+  if (n_envs == 0) return IGI_OK;
+  CompactParams p{};
+  p.depth = depth; p.seg = seg; p.uvx = uvx; p.uvy = uvy; p.uvz = uvz; p.ext = ext; p.e2g_inv = e2g_inv;
+  p.out_pts = out_pts; p.out_count = out_count; p.out_any = out_any;
+  p.n_envs = n_envs; p.H = H; p.W = W; p.n_classes = n_classes;
+  for (int c = 0; c < n_classes; ++c) p.seg_ids[c] = seg_ids ? seg_ids[c] : 0;
+  p.depth_max = depth_max;
+  p.has_box = box != nullptr;
+  if (box) for (int i = 0; i < 6; ++i) p.box[i] = box[i];
+  const size_t npix = (size_t)H * W;
+  const size_t smem = npix * 8;
+  IGI_REQUIRE(smem <= 200 * 1024, "igi_pcl_compact: image too large for one CTA (%d x %d)", H, W);
+  p.use_bulk = ((npix * 4) % 16 == 0) && ((uintptr_t)depth % 16 == 0) && (!seg || (uintptr_t)seg % 16 == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    IGI_CUDA(cudaFuncSetAttribute(pcl_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  pcl_compact_kernel<<<n_envs, kCompactBlock, smem, (cudaStream_t)stream>>>(p);
+  IGI_CHECK_LAUNCH("pcl_compact_kernel");
+  return IGI_OK;
+}
+
+extern "C" int igi_pcl_sample_gather(const float* pts, const int32_t* count, const int32_t* any,
+                                     int n_classes, int cls, int cap, const uint32_t* raw, int n_envs, int m,
+                                     float* out, int64_t out_stride, int32_t* out_idx, int32_t* out_consumed,
+                                     int32_t* scratch_offsets, void* stream) {
+  IGI_REQUIRE(pts && count && any && raw && out && scratch_offsets, "igi_pcl_sample_gather: null pointer");
+  IGI_REQUIRE(n_classes >= 1 && cls >= 0 && cls < n_classes && cap > 0 && m > 0 && n_envs >= 0,
+              "igi_pcl_sample_gather: bad dims");
+  IGI_REQUIRE(out_stride >= (int64_t)m * 3, "igi_pcl_sample_gather: out_stride < 3*m");
+  if (n_envs == 0) return IGI_OK;
+  int32_t* d_offsets = scratch_offsets;
+  cudaStream_t s = (cudaStream_t)stream;
+  pcl_offsets_kernel<<<1, 1024, 0, s>>>(any, n_classes, cls, n_envs, m, d_offsets, out_consumed);
+  IGI_CHECK_LAUNCH("pcl_offsets_kernel");
+  pcl_gather_kernel<<<n_envs, 128, 0, s>>>(pts, count, any, n_classes, cls, cap, raw, d_offsets, m, out,
+                                            out_stride, out_idx);
+  IGI_CHECK_LAUNCH("pcl_gather_kernel");
+  return IGI_OK;
+}
+
+extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
+                       int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts,
+                       int64_t out_stride, int32_t* out_idx, void* stream) {
+  IGI_REQUIRE(pts && (out_pts || out_idx), "igi_fps: null pointer");
+  IGI_REQUIRE(n_tasks >= 0 && m > 0, "igi_fps: bad dims");
+  IGI_REQUIRE(count || n_fixed > 0, "igi_fps: need count or n_fixed");
+  IGI_REQUIRE(!out_pts || out_stride >= (int64_t)m * 3, "igi_fps: out_stride < 3*m");
+  if (n_tasks == 0) return IGI_OK;
+  // worst-case dynamic smem: task_stride/3 points (count is on the device)
+  const int64_t nmax = count ? task_stride / 3 : n_fixed;
+  IGI_REQUIRE(nmax <= 0xffff, "igi_fps: at most 65535 points per task");
+  const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
+  IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  fps_kernel<<<n_tasks, kFpsBlock, smem, (cudaStream_t)stream>>>(pts, task_stride, count, any, count_stride,
+                                                                 n_fixed, m, out_pts, out_stride, out_idx);
+  IGI_CHECK_LAUNCH("fps_kernel");
+  return IGI_OK;
+}

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Path of libigi_b200.so; built here when nvcc is available and it is stale/missing."""
+    import shutil
+    from isaacgyminsertion_b200 import build
+    if shutil.which("nvcc"):
+        build.build()
+    assert os.path.exists(build.LIB), "libigi_b200.so missing and nvcc not available"
+    return build.LIB

@@ -1,0 +1,130 @@
+"""CPU: the (P) oracle against golden vectors produced by the REAL reference classes
+(tools/make_golden_pcl.py), plus the host-side RNG mirror and the FPS oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from isaacgyminsertion_b200 import synthetic
+from isaacgyminsertion_b200.pcl_utils import TorchCpuRandintStream, uv_table, filter_pts as box_filter
+from oracle import fps as ofps
+from oracle import pcl as opcl
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "pcl_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def scene(golden):
+    gym = synthetic.SyntheticGym(golden["depth"].shape[0], seed=int(golden["seed"]))
+    return gym, opcl.build_cameras(gym)
+
+
+def test_synthetic_frames_are_reproducible(golden):
+    N = golden["depth"].shape[0]
+    gym = synthetic.SyntheticGym(N, seed=3)
+    pp, pq, sp = synthetic.scene_poses(N, seed=3)
+    depth, seg = synthetic.external_camera_frames(gym, pp, pq, sp, seed=3)
+    keep = [e for e in range(N) if e not in (5, 6, 7, 8)]
+    assert np.array_equal(depth[keep], golden["depth"][keep])
+    assert np.array_equal(seg[keep], golden["seg"][keep])
+
+
+def test_camera_tables_match_reference(golden, scene):
+    gym, cams = scene
+    assert np.array_equal(cams[0].uv_one_in_cam.numpy(), golden["uv_table0"])
+    assert np.array_equal(cams[0].ext_mat.numpy(), golden["ext0"])
+    assert np.array_equal(uv_table(gym.get_camera_proj_matrix(None, 0, 0), gym.width, gym.height).numpy(),
+                          golden["uv_table0"])
+
+
+def test_convert_matches_reference(golden, scene):
+    _, cams = scene
+    pts = cams[0].convert(torch.from_numpy(golden["depth"][0]))
+    assert np.array_equal(pts.numpy(), golden["unfiltered0"])
+
+
+def test_point_cloud_matches_reference_bit_exact(golden, scene):
+    _, cams = scene
+    depth = torch.from_numpy(golden["depth"])
+    seg = torch.from_numpy(golden["seg"])
+    torch.manual_seed(42)
+    plug, _, plug_all = opcl.get_point_cloud(cams, opcl.masked_depth(depth, seg, 2), 400, return_idx=True)
+    socket, _, socket_all = opcl.get_point_cloud(cams, opcl.masked_depth(depth, seg, 3), 400, return_idx=True)
+    probe = torch.randint(0, 1 << 20, (8,))
+    assert np.array_equal(np.array([len(p) for p in plug_all]), golden["plug_counts"])
+    assert np.array_equal(np.array([len(p) for p in socket_all]), golden["socket_counts"])
+    assert np.array_equal(torch.cat(plug_all).numpy(), golden["plug_all"])
+    assert np.array_equal(torch.cat(socket_all).numpy(), golden["socket_all"])
+    assert np.array_equal(plug.numpy(), golden["plug"])
+    assert np.array_equal(socket.numpy(), golden["socket"])
+    assert np.array_equal(probe.numpy(), golden["rng_probe"])
+    # degenerate envs: empty cloud -> all zeros (pcl_utils.py:175,179-183)
+    assert not plug[5].any() and not plug[6].any() and not socket[7].any()
+
+
+def test_box_filter_equals_reference_filter():
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand((5000, 3), generator=g) * torch.tensor([1.0, 1.2, 0.8]) - torch.tensor([0.1, 0.6, 0.1])
+    pts[:5] = torch.tensor([[0.1, -0.4, 0.001], [0.7, 0.4, 0.6], [0.7001, 0, 0.1], [0.3, 0, 0.0009], [0.3, 0.41, 0.2]])
+    assert torch.equal(box_filter(pts), opcl.filter_pts(pts))
+
+
+def test_rng_stream_mirror_matches_torch_randint():
+    """`torch.randint(0, n, (m,))` == raw MT19937 words % n, and commit() advances torch identically."""
+    stream = TorchCpuRandintStream()
+    torch.manual_seed(1234)
+    torch.rand(7)  # arbitrary position inside the state block
+    counts = [1, 5, 399, 400, 5184, 77, 1000, 3]
+    raw = stream.peek(len(counts) * 400)
+    mine = [raw[i * 400:(i + 1) * 400].astype(np.int64) % c for i, c in enumerate(counts)]
+    ref = [torch.randint(0, c, (400,)).numpy() for c in counts]
+    for a, b in zip(mine, ref):
+        assert np.array_equal(a, b)
+    after_ref = torch.randint(0, 1 << 20, (16,))
+    torch.manual_seed(1234)
+    torch.rand(7)
+    stream.commit(len(counts) * 400)
+    after_mine = torch.randint(0, 1 << 20, (16,))
+    assert torch.equal(after_ref, after_mine)
+
+
+def test_rng_stream_crosses_state_regeneration():
+    stream = TorchCpuRandintStream()
+    torch.manual_seed(7)
+    raw = stream.peek(2000)  # > 624 words: crosses three twists
+    ref = torch.randint(0, 1000, (2000,)).numpy()
+    assert np.array_equal(raw.astype(np.int64) % 1000, ref)
+
+
+def test_fps_oracle_properties():
+    rng = np.random.default_rng(0)
+    pts = (rng.random((300, 3)) + 0.2).astype(np.float32)
+    idx = ofps.furthest_point_sample(pts, 64)
+    assert idx[0] == 0 and len(set(idx.tolist())) == 64
+    # second pick is the farthest point from point 0
+    d = ((pts - pts[0]) ** 2).sum(1)
+    assert idx[1] == int(np.argmax(d))
+    # min pairwise distance of the picks is non-increasing in pick order (FPS property)
+    cover = []
+    for j in range(1, 64):
+        dj = ((pts[idx[:j]] - pts[idx[j]]) ** 2).sum(1).min()
+        cover.append(dj)
+    assert all(cover[i] >= cover[i + 1] - 1e-7 for i in range(len(cover) - 1))
+
+
+def test_fps_oracle_degenerate():
+    pts = np.full((5, 3), 0.5, dtype=np.float32)
+    pts[3] = [0.9, 0.5, 0.5]
+    idx = ofps.furthest_point_sample(pts, 6)
+    assert idx[0] == 0 and idx[1] == 3
+    # all remaining distances are 0: tie rule (B=4): bit-reversed (k mod 4) then k -> k=0 (rev 0)
+    assert idx[2] == 0
+    # points near the origin never become candidates -> index 0 forever
+    z = np.zeros((4, 3), dtype=np.float32)
+    assert ofps.furthest_point_sample(z, 3).tolist() == [0, 0, 0]
+    out, idx = ofps.fps_batch([np.zeros((0, 3)), pts], 4)
+    assert not out[0].any() and idx[1][1] == 3

@@ -1,0 +1,161 @@
+"""GPU parity: the sm_100a (P) kernels through the C-ABI against the CPU oracle and the
+golden vectors of the real reference.
+
+Tolerances (north star): segmentation masks, counts, sample / FPS indices bit-exact;
+point coordinates within 1e-5 relative.  The reference evaluates `pts @ inv(view)` in
+GLOBAL coordinates and then subtracts the env origin (pcl_utils.py:83-85), so the relative
+bound applies to the global-coordinate magnitude: atol = 1e-5 * max|global coordinate|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from isaacgyminsertion_b200 import synthetic
+from oracle import fps as ofps
+from oracle import pcl as opcl
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(gym):
+    return 1e-5 * float(np.abs(gym.origins).max() + 1.0)
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "pcl_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def cam(golden, built_lib):
+    from isaacgyminsertion_b200.pcl_utils import CameraPointCloud, filter_pts
+    gym = synthetic.SyntheticGym(golden["depth"].shape[0], seed=int(golden["seed"]))
+    gen = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props, sample_num=400,
+                           filter_func=filter_pts, pt_in_local=True, graphics_device="cuda:0",
+                           compute_device="cuda:0")
+    return gym, gen
+
+
+def test_golden_reference_sampler(golden, cam):
+    gym, gen = cam
+    depth = torch.from_numpy(golden["depth"]).cuda()
+    seg = torch.from_numpy(golden["seg"]).cuda()
+    N = depth.shape[0]
+    torch.manual_seed(42)
+    plug_depth = (depth.flatten(1) * (seg.flatten(1) == 2)).reshape(N, gym.height, gym.width)
+    plug = gen.get_point_cloud(plug_depth, sample_num=400)
+    # fused masking variant for the socket
+    socket = gen.get_point_cloud(depth, sample_num=400, seg=seg, seg_id=3)
+    probe = torch.randint(0, 1 << 20, (8,))
+    tol = _tol(gym)
+    np.testing.assert_allclose(plug.cpu().numpy(), golden["plug"], rtol=1e-5, atol=tol)
+    np.testing.assert_allclose(socket.cpu().numpy(), golden["socket"], rtol=1e-5, atol=tol)
+    assert np.array_equal(probe.numpy(), golden["rng_probe"]), "CPU generator not advanced like the reference"
+    assert not plug[5].any() and not plug[6].any() and not socket[7].any()
+
+
+def test_golden_compaction_counts_and_order(golden, cam):
+    gym, gen = cam
+    depth = torch.from_numpy(golden["depth"]).cuda()
+    seg = torch.from_numpy(golden["seg"]).cuda()
+    from isaacgyminsertion_b200.pcl_utils import filter_pts
+    pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3), filter_pts.box)
+    cnt = cnt.cpu().numpy()
+    assert np.array_equal(cnt[:, 0], golden["plug_counts"])
+    assert np.array_equal(cnt[:, 1], golden["socket_counts"])
+    assert np.array_equal(any_.cpu().numpy(), (cnt > 0).astype(np.int32))
+    got = torch.cat([pts[e, 0, :cnt[e, 0]] for e in range(len(cnt))]).cpu().numpy()
+    np.testing.assert_allclose(got, golden["plug_all"], rtol=1e-5, atol=_tol(gym))
+    got = torch.cat([pts[e, 1, :cnt[e, 1]] for e in range(len(cnt))]).cpu().numpy()
+    np.testing.assert_allclose(got, golden["socket_all"], rtol=1e-5, atol=_tol(gym))
+
+
+def test_get_ptd_cuda_and_convert(golden, cam):
+    gym, gen = cam
+    from isaacgyminsertion_b200.pcl_utils import PointCloudGenerator
+    depth = torch.from_numpy(golden["depth"]).cuda()
+    lst = gen.get_ptd_cuda(depth[:3], env_ids=[0, 1, 2], filter_func=None)
+    np.testing.assert_allclose(lst[0].cpu().numpy(), golden["unfiltered0"], rtol=1e-5, atol=_tol(gym))
+    o = gym.get_env_origin(0)
+    e2g = np.identity(4)
+    e2g[:3, 3] = [o.x, o.y, o.z]
+    g1 = PointCloudGenerator(gym.get_camera_proj_matrix(None, 0, 0), gym.get_camera_view_matrix(None, 0, 0),
+                             e2g, camera_props=gym.camera_props[0], depth_max=1.0, device="cuda:0")
+    np.testing.assert_allclose(g1.convert(depth[0]).cpu().numpy(), golden["unfiltered0"], rtol=1e-5,
+                               atol=_tol(gym))
+
+
+@pytest.mark.parametrize("n_envs,seed", [(1, 0), (67, 1), (300, 2)])
+def test_seeded_scenes_vs_oracle(built_lib, n_envs, seed):
+    from isaacgyminsertion_b200.pcl_utils import CameraPointCloud, filter_pts
+    gym = synthetic.SyntheticGym(n_envs, seed=seed)
+    pp, pq, sp = synthetic.scene_poses(n_envs, seed=seed)
+    depth, seg = synthetic.external_camera_frames(gym, pp, pq, sp, seed=seed)
+    cams = opcl.build_cameras(gym)
+    d_t, s_t = torch.from_numpy(depth), torch.from_numpy(seg)
+    torch.manual_seed(5)
+    want = opcl.pcl_observation(cams, d_t, s_t)
+    gen = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props, sample_num=400,
+                           filter_func=filter_pts, pt_in_local=True, graphics_device="cuda:0",
+                           compute_device="cuda:0")
+    torch.manual_seed(5)
+    plug = gen.get_point_cloud(d_t.cuda(), seg=s_t.cuda(), seg_id=2)
+    socket = gen.get_point_cloud(d_t.cuda(), seg=s_t.cuda(), seg_id=3)
+    got = torch.cat([plug, socket], dim=1).flatten(1).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=_tol(gym))
+
+
+def test_fps_pipeline_indices_bit_exact(golden, cam):
+    gym, gen = cam
+    from isaacgyminsertion_b200.pcl_utils import filter_pts
+    depth = torch.from_numpy(golden["depth"]).cuda()
+    seg = torch.from_numpy(golden["seg"]).cuda()
+    pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3), filter_pts.box)
+    for cls in (0, 1):
+        out, idx = gen.engine.sample_fps(pts, cnt, any_, cls, 400, return_idx=True)
+        c = cnt[:, cls].cpu().numpy()
+        lst = [pts[e, cls, :c[e]].cpu().numpy() for e in range(len(c))]
+        want_pts, want_idx = ofps.fps_batch(lst, 400)
+        assert np.array_equal(idx.cpu().numpy(), want_idx)
+        assert np.array_equal(out.cpu().numpy(), want_pts)
+
+
+@pytest.mark.parametrize("n,m", [(1, 4), (2, 5), (37, 16), (400, 400), (513, 64), (5184, 400)])
+def test_fps_standalone(built_lib, n, m):
+    from isaacgyminsertion_b200.pcl_utils import furthest_point_sample
+    rng = np.random.default_rng(n)
+    B = 5
+    pts = (rng.random((B, n, 3)) * 0.5 + 0.1).astype(np.float32)
+    if n >= 37:
+        pts[1, n // 2:] = pts[1, : n - n // 2]      # duplicated points -> exact distance ties
+        pts[2, :] = pts[2, 0]                       # all identical
+        pts[3, ::3] = 0.0                           # |p|^2 <= 1e-3: never candidates
+    idx = furthest_point_sample(torch.from_numpy(pts).cuda(), m).cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(idx[b], ofps.furthest_point_sample(pts[b], m)), f"batch {b}"
+
+
+def test_non_tma_path_matches(built_lib):
+    """H*W*4 not a multiple of 16 -> plain loads instead of the bulk-copy path."""
+    from isaacgyminsertion_b200.pcl_utils import BatchedPointCloud
+    gym = synthetic.SyntheticGym(9, seed=4, width=45, height=31)
+    pp, pq, sp = synthetic.scene_poses(9, seed=4)
+    depth, seg = synthetic.external_camera_frames(gym, pp, pq, sp, seed=4)
+    cams = opcl.build_cameras(gym)
+    eng = BatchedPointCloud(gym._proj, gym._view, [np.block([[np.eye(3), gym.origins[e][:, None]],
+                                                             [np.zeros((1, 3)), np.ones((1, 1))]])
+                                                   for e in range(9)], 45, 31, device="cuda:0")
+    pts, cnt, _ = eng.compact(torch.from_numpy(depth).cuda(), torch.from_numpy(seg).cuda(), (2,),
+                              opcl_box())
+    want = opcl.get_ptd(cams, opcl.masked_depth(torch.from_numpy(depth), torch.from_numpy(seg), 2))
+    assert [len(w) for w in want] == cnt[:, 0].tolist()
+    for e in range(9):
+        np.testing.assert_allclose(pts[e, 0, :len(want[e])].cpu().numpy(), want[e].numpy(), rtol=1e-5,
+                                   atol=_tol(gym))
+
+
+def opcl_box():
+    from isaacgyminsertion_b200.pcl_utils import filter_pts
+    return filter_pts.box
