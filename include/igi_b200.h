@@ -89,6 +89,111 @@ int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const i
             int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts, int64_t out_stride,
             int32_t* out_idx, void* stream);
 
+/* --------------------------------------------------------------------------
+ * (T) allsight tactile renderer
+ * -------------------------------------------------------------------------- */
+
+/* Sensor constants (host memory; copied to __constant__).  Values come from the sensor
+ * yaml the reference loads at tacto/renderer.py:86-87 (config_allsight_white.yml) and from
+ * tacto_allsight_wrapper/allsight_wrapper.py:100-174 (spot lights), expressed in the
+ * CAMERA frame (camera at the origin looking down -z, OpenGL convention). */
+typedef struct IgiSensorParams {
+  int32_t width, height;        /* 224 x 224 (FactoryTaskInsertionTactile.yaml:31-33) */
+  float znear;                  /* yml camera.znear */
+  const float* dxp;             /* (width)  ray slope per column: ((px+.5)/W*2-1)*tan(yfov/2)*aspect */
+  const float* dyp;             /* (height) ray slope per row:    (1-(py+.5)/H*2)*tan(yfov/2)        */
+  int32_t n_lights;
+  const float* light_pos;       /* (L,3) */
+  const float* light_dir;       /* (L,3) unit spot direction */
+  const float* light_col;       /* (L,3) */
+  const float* light_int;       /* (L)   */
+  const float* light_las;       /* (L) 1/max(.001, cos(inner)-cos(outer)) */
+  const float* light_lao;       /* (L) -cos(outer)*las */
+  int32_t inverse_square;       /* 1: radiance / d^2 ; 0: none (yaml lights.falloff) */
+  float base_color[3], metallic, roughness;
+  double cam_R[9], cam_p[3];    /* camera zero pose in the sensor frame (renderer.py:305-311) */
+  double max_force, max_deformation; /* yml force.range_force[1], force.max_deformation */
+  float calib_scale, clip_lo, clip_hi; /* yml bg_calibration */
+  int32_t blur_ksize;           /* 7 */
+  float gauss[7];               /* cv2.getGaussianKernel(7, sigma) */
+  float grid_org[3], grid_h, grid_slack; /* conservative gel-interior distance grid */
+  int32_t grid_n[3];
+  float depth0_max;
+  float area_w_full, area_w_half; /* cv2 INTER_AREA 3.5x taps as float32: 2/7 and 1/7 */
+} IgiSensorParams;
+
+/* Mesh table (device): all plug meshes concatenated, faces grouped into clusters. */
+typedef struct IgiTactileMeshes {
+  const float* verts;           /* (nv,3) object frame, x,y pre-scaled (allsight_render.py:101-107) */
+  const float* vnorm;           /* (nv,3) vertex normals */
+  const int32_t* faces;         /* (nf,3) vertex ids into verts, cluster order */
+  const int32_t* face_orig;     /* (nf) original face index inside its mesh (depth-tie order) */
+  const int32_t* meshes;        /* (n_meshes,4) face_off, n_faces, cluster_off, n_clusters */
+  const void* clusters;         /* (n_clusters) {float cx,cy,cz,r; int first,count,pad,pad} */
+} IgiTactileMeshes;
+
+/* Static per-sensor-type images (device). */
+typedef struct IgiTactileStatic {
+  const float* depth0;          /* (H,W)   gel depth, get_background_sim renderer.py:165-168 */
+  const uint8_t* bg_sim;        /* (H,W,3) raw gel render */
+  const uint8_t* bg_real;       /* (n_bg,H,W,3) real reference frames, renderer.py:555-558 */
+  const float* obs_empty;       /* (2048)  observation of a no-contact frame */
+  const float* grid;            /* (nz,ny,nx) distance grid */
+} IgiTactileStatic;
+
+/* Per-step inputs (device): poses exactly as update_tactile gathers them
+ * (factory_task_insertion.py:481-484), frame f = env*sensors_per_env + sensor. */
+typedef struct IgiTactileFrames {
+  int32_t n_envs, sensors_per_env;
+  const float* finger_pos;      /* (n_envs*S,3) */
+  const float* finger_quat;     /* (n_envs*S,4) xyzw */
+  const float* plug_pos;        /* (n_envs,3) */
+  const float* plug_quat;       /* (n_envs,4) xyzw */
+  const float* force;           /* (n_envs*S) normal force or NULL -> force_const (70, task :535) */
+  float force_const;
+  const uint8_t* update;        /* (n_envs) update_freq & update_delay or NULL (all) (task :523) */
+  const int32_t* mesh_id;       /* (n_envs) */
+  const int32_t* bg_id;         /* (n_envs*S) index into bg_real */
+} IgiTactileFrames;
+
+typedef struct IgiTactileScratch {
+  float* M;                     /* (F,12) object->camera matrices */
+  void* setups;                 /* (F,kmax) 64-byte triangle setup records */
+  int32_t* counts;              /* (F) */
+  int32_t* bbox;                /* (F,4) */
+  int32_t* worklist;            /* (F) */
+  int32_t* counters;            /* (4): work_n, cursor, overflow (sticky), reserved */
+  int32_t kmax;                 /* <= 4096 */
+} IgiTactileScratch;
+
+typedef struct IgiTactileOut {
+  uint8_t* color;               /* (F,H,W,3) calibrated tactile image, AllSightRenderer.render()[0] */
+  float* gel_depth;             /* (F,H,W)   depth0 - depth,           AllSightRenderer.render()[1] */
+  float* obs;                   /* frame f at obs + f*obs_stride: (2048) f32 = tactile_imgs[e,n] (task :574) */
+  int64_t obs_stride;
+} IgiTactileOut;
+
+/* Upload sensor constants.  Replaces Renderer.__init__/_init_camera/_init_light
+ * (tacto/renderer.py:65-163,291-325; allsight_wrapper.py:100-174). */
+int igi_tactile_set_sensor(const IgiSensorParams* p);
+
+/* K0: depth0 + bg_sim of the static gel.  Replaces get_background_sim (renderer.py:165-168).
+ * gel_tris (n,3,3) f32 sensor frame; scratch_zbuf (H*W) u64. */
+int igi_tactile_gel_precompute(const float* gel_tris, int n_tris, uint64_t* scratch_zbuf, float* depth0,
+                               uint8_t* bg_sim, void* stream);
+
+/* K1+K2+K3 for every env x sensor frame.  Replaces the hot loop of _render_tactile
+ * (factory_task_insertion.py:515-583): update_pose_given_sim_pose (allsight_render.py:168-172),
+ * AllSightRenderer.render (:179-212) -> Renderer.render/adjust_with_force/pyrender draw
+ * (tacto/renderer.py:560-648), _calibrate (allsight_wrapper.py:57-98), depth0-depth, remove_bg,
+ * mask, flipud, crop, INTER_AREA resize, gray (task :546-574). */
+int igi_tactile_render(const IgiTactileMeshes* meshes, const IgiTactileStatic* st, const IgiTactileFrames* frames,
+                       const IgiTactileScratch* scratch, const IgiTactileOut* out, void* stream);
+
+/* K3 alone: color (F,H,W,3) u8 -> obs.  Replaces factory_task_insertion.py:546-574. */
+int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,
+                    int64_t obs_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,787 @@
+// (T) allsight tactile renderer, batched over env x fingertip sensor frames.
+//
+//   K0  tac_gel_raster / tac_gel_shade   static gel: depth0 + bg_sim (once)
+//   K1a tac_geom       per frame: f64 pose chain, cluster + triangle cull against the gel
+//                      interior, triangle setup records, contact worklist
+//   K2f tac_fill       every live frame: color = bg_real, gel_depth = 0, obs = obs_empty
+//                      (pure 128-bit streaming stores; the no-contact result is exact)
+//   K1b/K2/K3 tac_contact  frames with surviving triangles: tile z-buffer raster in shared
+//                      memory, PBR shade, (c - bg_sim)*s, 7x7 Gaussian, + bg_real, clip ->
+//                      color; depth0 - depth; then the obs pixels the dirty window touches
+//
+// Raster arithmetic follows the contract in oracle/raster.c / DESIGN.md "raster spec":
+// f32, every operation rounded separately (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn), same
+// order, so coverage and depth are bit-identical to the oracle.
+#include "igi_common.cuh"
+#include "../../include/igi_b200.h"
+
+namespace {
+
+constexpr int TW = 224, TH = 224;       // tactile image
+constexpr int OBS_W = 64, OBS_H = 32;   // encoder image after crop
+constexpr int MAX_LIGHTS = 8;
+constexpr int TILE = 32, HALO = 3, REG = TILE + 2 * HALO;  // contact tile + blur halo
+constexpr uint64_t ZEMPTY = 0xffffffffffffffffull;
+
+struct TacConst {
+  float znear;
+  int n_lights;
+  float light_pos[MAX_LIGHTS][3], light_dir[MAX_LIGHTS][3], light_col[MAX_LIGHTS][3];
+  float light_int[MAX_LIGHTS], light_las[MAX_LIGHTS], light_lao[MAX_LIGHTS];
+  int inverse_square;
+  float base[3], metallic, roughness;
+  double cam_R[9], cam_p[3];  // camera zero pose in the sensor frame
+  float gel_camx;
+  double max_force, max_deformation;
+  float calib_scale, clip_lo, clip_hi;
+  float gauss[7];
+  // conservative gel-interior distance grid (camera frame, metres)
+  float grid_org[3], grid_h, grid_slack;
+  int grid_n[3];
+  float depth0_max;
+  float area_w[5];  // INTER_AREA 3.5x taps (f32 as cv2 stores them): even dst: w0 w0 w0 w1, odd: w1 w0 w0 w0
+};
+__constant__ TacConst kc;
+__constant__ float k_dxp[TW];
+__constant__ float k_dyp[TH];
+
+// ---- spec arithmetic ---------------------------------------------------------------
+struct V3 { float x, y, z; };
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dot3s(V3 a, V3 b) { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
+__device__ __forceinline__ V3 cross3s(V3 a, V3 b) {
+  return V3{sub(mul(a.y, b.z), mul(a.z, b.y)), sub(mul(a.z, b.x), mul(a.x, b.z)), sub(mul(a.x, b.y), mul(a.y, b.x))};
+}
+__device__ __forceinline__ V3 xform(const float* M, V3 v) {
+  V3 o;
+  o.x = add(add(add(mul(M[0], v.x), mul(M[1], v.y)), mul(M[2], v.z)), M[3]);
+  o.y = add(add(add(mul(M[4], v.x), mul(M[5], v.y)), mul(M[6], v.z)), M[7]);
+  o.z = add(add(add(mul(M[8], v.x), mul(M[9], v.y)), mul(M[10], v.z)), M[11]);
+  return o;
+}
+__device__ __forceinline__ V3 gel_to_cam(const float* v, float camx) { return V3{-v[1], v[2], -sub(v[0], camx)}; }
+__device__ __forceinline__ bool owns_zero(V3 n) {
+  if (n.x != 0.0f) return n.x > 0.0f;
+  if (n.y != 0.0f) return n.y > 0.0f;
+  return n.z > 0.0f;
+}
+__device__ __forceinline__ float edge_fn(float dx, float dy, V3 n) { return sub(add(mul(dx, n.x), mul(dy, n.y)), n.z); }
+__device__ __forceinline__ bool edge_in(float e, V3 n) { return e < 0.0f || (e == 0.0f && owns_zero(n)); }
+
+struct Setup {       // 64 B record
+  V3 n0, n1, n2, N;  // edge-plane normals BxC, CxA, AxB and face normal (B-A)x(C-A)
+  float det;         // N.A  (< 0: front-facing)
+  uint32_t bbox;     // x0 | y0<<8 | x1<<16 | y1<<24 (pixels, inclusive, conservative)
+  uint32_t tri;      // face index in the (cluster-ordered) mesh face table
+  uint32_t orig;     // original face index (depth-tie order)
+};
+static_assert(sizeof(Setup) == 64, "setup record must be 64 B");
+
+__device__ __forceinline__ bool make_setup(V3 A, V3 B, V3 C, Setup& s) {
+  V3 E1{sub(B.x, A.x), sub(B.y, A.y), sub(B.z, A.z)};
+  V3 E2{sub(C.x, A.x), sub(C.y, A.y), sub(C.z, A.z)};
+  s.N = cross3s(E1, E2);
+  s.det = dot3s(s.N, A);
+  if (!(s.det < 0.0f)) return false;
+  s.n0 = cross3s(B, C);
+  s.n1 = cross3s(C, A);
+  s.n2 = cross3s(A, B);
+  return true;
+}
+
+// Conservative pixel bbox of the part of the triangle at depth >= znear. Returns false if empty.
+__device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
+  const float zn = kc.znear;
+  float zA = -A.z, zB = -B.z, zC = -C.z;
+  if (fmaxf(zA, fmaxf(zB, zC)) < zn) return false;
+  float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+  V3 P[3] = {A, B, C};
+  float Z[3] = {zA, zB, zC};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int j = (i + 1) % 3;
+    if (Z[i] >= zn) {
+      float sx = P[i].x / Z[i], sy = P[i].y / Z[i];
+      mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+    }
+    if ((Z[i] >= zn) != (Z[j] >= zn)) {  // edge crosses the near plane: add the crossing point
+      float t = (zn - Z[i]) / (Z[j] - Z[i]);
+      float sx = (P[i].x + t * (P[j].x - P[i].x)) / zn, sy = (P[i].y + t * (P[j].y - P[i].y)) / zn;
+      mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+    }
+  }
+  const float sx0 = k_dxp[0], sx1 = k_dxp[TW - 1], sy0 = k_dyp[0], sy1 = k_dyp[TH - 1];
+  const float kx = (float)(TW - 1) / (sx1 - sx0), ky = (float)(TH - 1) / (sy1 - sy0);
+  float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
+  float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
+  if (fx1 < -2.0f || fy1 < -2.0f || fx0 > (float)(TW + 1) || fy0 > (float)(TH + 1)) return false;
+  x0 = (int)fmaxf(floorf(fx0) - 1.0f, 0.0f);
+  y0 = (int)fmaxf(floorf(fy0) - 1.0f, 0.0f);
+  x1 = (int)fminf(ceilf(fx1) + 1.0f, (float)(TW - 1));
+  y1 = (int)fminf(ceilf(fy1) + 1.0f, (float)(TH - 1));
+  return x0 <= x1 && y0 <= y1;
+}
+
+// coverage + depth of one pixel; returns t (depth) or -1 when not covered / clipped
+__device__ __forceinline__ float cover(const Setup& s, int px, int py, float& e1, float& e2, float& esum) {
+  const float dx = k_dxp[px], dy = k_dyp[py];
+  const float e0 = edge_fn(dx, dy, s.n0);
+  if (!edge_in(e0, s.n0)) return -1.0f;
+  e1 = edge_fn(dx, dy, s.n1);
+  if (!edge_in(e1, s.n1)) return -1.0f;
+  e2 = edge_fn(dx, dy, s.n2);
+  if (!edge_in(e2, s.n2)) return -1.0f;
+  const float den = edge_fn(dx, dy, s.N);
+  const float t = __fdiv_rn(s.det, den);
+  if (!(t >= kc.znear)) return -1.0f;
+  esum = add(add(e0, e1), e2);
+  return t;
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ V3 normalize(V3 v) {
+  float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+  if (l > 0.0f) { float r = 1.0f / l; v.x *= r; v.y *= r; v.z *= r; }
+  return v;
+}
+
+// pyrender mesh.frag (metallic-roughness, spot lights) -> 8-bit UNORM rgb
+__device__ void shade(V3 p, V3 n, uint8_t* rgb) {
+  const float PI = 3.14159265358979323846f;
+  V3 v = normalize(V3{-p.x, -p.y, -p.z});
+  float f0[3], cdiff[3], col[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    f0[k] = 0.04f * (1.0f - kc.metallic) + kc.base[k] * kc.metallic;
+    cdiff[k] = kc.base[k] * (1.0f - 0.04f) * (1.0f - kc.metallic);
+  }
+  const float f90 = clampf(fmaxf(fmaxf(f0[0], f0[1]), f0[2]) * 25.0f, 0.0f, 1.0f);
+  const float alpha = kc.roughness * kc.roughness, a2 = alpha * alpha;
+  for (int i = 0; i < kc.n_lights; ++i) {
+    V3 L{kc.light_pos[i][0] - p.x, kc.light_pos[i][1] - p.y, kc.light_pos[i][2] - p.z};
+    const float d2 = L.x * L.x + L.y * L.y + L.z * L.z;
+    V3 l = normalize(L);
+    V3 h = normalize(V3{l.x + v.x, l.y + v.y, l.z + v.z});
+    const float nl = clampf(n.x * l.x + n.y * l.y + n.z * l.z, 0.001f, 1.0f);
+    const float nv = clampf(n.x * v.x + n.y * v.y + n.z * v.z, 0.001f, 1.0f);
+    const float nh = clampf(n.x * h.x + n.y * h.y + n.z * h.z, 0.001f, 1.0f);
+    const float vh = clampf(v.x * h.x + v.y * h.y + v.z * h.z, 0.001f, 1.0f);
+    const float cd = -(kc.light_dir[i][0] * l.x + kc.light_dir[i][1] * l.y + kc.light_dir[i][2] * l.z);
+    float att = clampf(cd * kc.light_las[i] + kc.light_lao[i], 0.0f, 1.0f);
+    att = att * att;
+    if (kc.inverse_square) att = att / d2;
+    const float w = clampf(1.0f - vh, 0.0f, 1.0f);
+    const float w2 = w * w, fw = w2 * w2 * w;
+    const float al = 2.0f * nl / (nl + sqrtf(a2 + (1.0f - a2) * (nl * nl)));
+    const float av = 2.0f * nv / (nv + sqrtf(a2 + (1.0f - a2) * (nv * nv)));
+    const float G = al * av;
+    const float f = (nh * a2 - nh) * nh + 1.0f;
+    const float D = a2 / (PI * f * f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float F = f0[k] + (f90 - f0[k]) * fw;
+      const float diffuse = (1.0f - F) * cdiff[k] / PI;
+      const float spec = F * G * D / (4.0f * nl * nv);
+      col[k] += nl * (att * kc.light_col[i][k] * kc.light_int[i]) * (diffuse + spec);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float o = clampf(powf(col[k], 1.0f / 2.2f), 0.0f, 1.0f);
+    rgb[k] = (uint8_t)floorf(o * 255.0f + 0.5f);
+  }
+}
+
+// ---- K0: static gel -------------------------------------------------------------------
+__global__ void tac_gel_raster(const float* __restrict__ gel_tris, int G, unsigned long long* __restrict__ zbuf) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const float* t = gel_tris + (size_t)g * 9;
+  V3 A = gel_to_cam(t, kc.gel_camx), B = gel_to_cam(t + 3, kc.gel_camx), C = gel_to_cam(t + 6, kc.gel_camx);
+  Setup s;
+  if (!make_setup(A, B, C, s)) return;
+  int x0, y0, x1, y1;
+  if (!tri_bbox(A, B, C, x0, y0, x1, y1)) return;
+  for (int py = y0; py <= y1; ++py)
+    for (int px = x0; px <= x1; ++px) {
+      float e1, e2, es;
+      const float tt = cover(s, px, py, e1, e2, es);
+      if (tt < 0.0f) continue;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(tt) << 32) | (uint32_t)g;
+      atomicMin(zbuf + (size_t)py * TW + px, key);
+    }
+}
+
+__global__ void tac_gel_shade(const float* __restrict__ gel_tris, const unsigned long long* __restrict__ zbuf,
+                              float* __restrict__ depth0, uint8_t* __restrict__ bg_sim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= TW * TH) return;
+  const unsigned long long key = zbuf[i];
+  if (key == ZEMPTY) {
+    depth0[i] = 0.0f;
+    bg_sim[3 * i] = bg_sim[3 * i + 1] = bg_sim[3 * i + 2] = 255;
+    return;
+  }
+  const float t = __uint_as_float((uint32_t)(key >> 32));
+  const int g = (int)(key & 0xffffffffu);
+  depth0[i] = t;
+  const float* tp = gel_tris + (size_t)g * 9;
+  V3 A = gel_to_cam(tp, kc.gel_camx), B = gel_to_cam(tp + 3, kc.gel_camx), C = gel_to_cam(tp + 6, kc.gel_camx);
+  V3 E1{sub(B.x, A.x), sub(B.y, A.y), sub(B.z, A.z)}, E2{sub(C.x, A.x), sub(C.y, A.y), sub(C.z, A.z)};
+  V3 n = normalize(cross3s(E1, E2));
+  const int px = i % TW, py = i / TW;
+  V3 p{mul(k_dxp[px], t), mul(k_dyp[py], t), -t};
+  shade(p, n, bg_sim + 3 * i);
+}
+
+// ---- K1a: geometry ----------------------------------------------------------------------
+struct MeshInfo { int face_off, n_faces, cl_off, n_cl; };
+struct Cluster { float cx, cy, cz, r; int first, count, pad0, pad1; };
+
+struct GeomArgs {
+  const float* finger_pos;   // (F,3)   frame f = env*S + sensor
+  const float* finger_quat;  // (F,4) xyzw
+  const float* plug_pos;     // (N,3)
+  const float* plug_quat;    // (N,4)
+  const float* force;        // (F) or null -> force_const
+  const uint8_t* update;     // (N) or null
+  const int32_t* mesh_id;    // (N)
+  const MeshInfo* meshes;
+  const Cluster* clusters;
+  const float* verts;        // (nv,3) all meshes
+  const int32_t* faces;      // (nf,3) global vertex ids, cluster order
+  const int32_t* face_orig;  // (nf)
+  const float* grid;         // distance grid
+  float* M_out;              // (F,12)
+  Setup* setups;             // (F, kmax)
+  int32_t* counts;           // (F)   surviving triangles (may exceed kmax -> overflow)
+  int32_t* bbox;             // (F,4) dirty window x0,y0,x1,y1
+  int32_t* worklist;         // (F)
+  int32_t* work_n;           // (1)
+  int32_t* overflow;         // (1)
+  int sensors_per_env, kmax;
+  float force_const;
+};
+
+__device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid, float x, float y, float z) {
+  // lower bound of the distance from (x,y,z) (camera frame, depth = -z) to the gel interior
+  const float gx = x, gy = y, gz = -z;
+  const float lo0 = kc.grid_org[0], lo1 = kc.grid_org[1], lo2 = kc.grid_org[2];
+  const float h = kc.grid_h;
+  const float hi0 = lo0 + h * kc.grid_n[0], hi1 = lo1 + h * kc.grid_n[1], hi2 = lo2 + h * kc.grid_n[2];
+  const float cx = clampf(gx, lo0, hi0), cy = clampf(gy, lo1, hi1), cz = clampf(gz, lo2, hi2);
+  const float ddx = gx - cx, ddy = gy - cy, ddz = gz - cz;
+  const float dbox = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+  int ix = min(max((int)((cx - lo0) / h), 0), kc.grid_n[0] - 1);
+  int iy = min(max((int)((cy - lo1) / h), 0), kc.grid_n[1] - 1);
+  int iz = min(max((int)((cz - lo2) / h), 0), kc.grid_n[2] - 1);
+  const float d = grid[((size_t)iz * kc.grid_n[1] + iy) * kc.grid_n[0] + ix];
+  return fmaxf(dbox, d - kc.grid_slack - dbox);
+}
+
+constexpr int GEOM_BLOCK = 128;
+constexpr int GEOM_MAX_CL = 512;
+
+__global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
+  __shared__ float sM[12];
+  __shared__ int s_cl[GEOM_MAX_CL];
+  __shared__ int s_ncl, s_count;
+  __shared__ int s_bb[4];
+  const int f = blockIdx.x;
+  const int env = f / a.sensors_per_env;
+  const int tid = threadIdx.x;
+  if (a.update && !a.update[env]) {
+    if (tid == 0) a.counts[f] = -1;  // frame not rendered this step
+    return;
+  }
+  if (tid == 0) {
+    // ---- pose chain in f64 (xyzquat_to_tf_numpy, update_camera_pose_from_matrix, adjust_with_force)
+    double q[4], R[9], Ro[9];
+    const float* fq = a.finger_quat + (size_t)f * 4;
+    const float* fp = a.finger_pos + (size_t)f * 3;
+    const float* oq = a.plug_quat + (size_t)env * 4;
+    const float* op = a.plug_pos + (size_t)env * 3;
+    auto q2m = [](const float* qq, double* m) {
+      double x = qq[0], y = qq[1], z = qq[2], w = qq[3];
+      const double n = sqrt(x * x + y * y + z * z + w * w);
+      x /= n; y /= n; z /= n; w /= n;
+      const double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
+      const double xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
+      m[0] = x2 - y2 - z2 + w2; m[1] = 2 * (xy - zw);        m[2] = 2 * (xz + yw);
+      m[3] = 2 * (xy + zw);     m[4] = -x2 + y2 - z2 + w2;   m[5] = 2 * (yz - xw);
+      m[6] = 2 * (xz - yw);     m[7] = 2 * (yz + xw);        m[8] = -x2 - y2 + z2 + w2;
+    };
+    (void)q;
+    q2m(fq, R);
+    q2m(oq, Ro);
+    // camera world pose = T_finger * cam_zero
+    double Rc[9], pc[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j)
+        Rc[3 * i + j] = R[3 * i] * kc.cam_R[j] + R[3 * i + 1] * kc.cam_R[3 + j] + R[3 * i + 2] * kc.cam_R[6 + j];
+      pc[i] = R[3 * i] * kc.cam_p[0] + R[3 * i + 1] * kc.cam_p[1] + R[3 * i + 2] * kc.cam_p[2] + (double)fp[i];
+    }
+    const double force = a.force ? (double)a.force[f] : (double)a.force_const;
+    const double offset = fmin(kc.max_force, force) / kc.max_force;
+    double dir[3] = {pc[0] - (double)op[0], pc[1] - (double)op[1], pc[2] - (double)op[2]};
+    const double nrm = sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]) + 1e-6;
+    double po[3];
+    for (int i = 0; i < 3; ++i) po[i] = (double)op[i] + offset * kc.max_deformation * (dir[i] / nrm);
+    // M = inv(cam_world) * [Ro, po]
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j)
+        sM[4 * i + j] = (float)(Rc[i] * Ro[j] + Rc[3 + i] * Ro[3 + j] + Rc[6 + i] * Ro[6 + j]);
+      sM[4 * i + 3] = (float)(Rc[i] * (po[0] - pc[0]) + Rc[3 + i] * (po[1] - pc[1]) + Rc[6 + i] * (po[2] - pc[2]));
+    }
+    s_ncl = 0;
+    s_count = 0;
+    s_bb[0] = TW; s_bb[1] = TH; s_bb[2] = -1; s_bb[3] = -1;
+  }
+  __syncthreads();
+  if (tid < 12) a.M_out[(size_t)f * 12 + tid] = sM[tid];
+  const MeshInfo mi = a.meshes[a.mesh_id[env]];
+  // ---- cluster cull: bounding sphere against the gel-interior distance grid
+  for (int c = tid; c < mi.n_cl; c += GEOM_BLOCK) {
+    const Cluster cl = a.clusters[mi.cl_off + c];
+    V3 cc = xform(sM, V3{cl.cx, cl.cy, cl.cz});
+    if (grid_lower_bound(a.grid, cc.x, cc.y, cc.z) <= cl.r) {
+      const int slot = atomicAdd(&s_ncl, 1);
+      if (slot < GEOM_MAX_CL) s_cl[slot] = mi.cl_off + c;
+    }
+  }
+  __syncthreads();
+  const int ncl = min(s_ncl, GEOM_MAX_CL);
+  Setup* out = a.setups + (size_t)f * a.kmax;
+  // ---- triangles of surviving clusters: transform, back-face cull, interior test, setup
+  for (int c = 0; c < ncl; ++c) {
+    const Cluster cl = a.clusters[s_cl[c]];
+    for (int k = tid; k < cl.count; k += GEOM_BLOCK) {
+      const int face = cl.first + k;
+      const int i0 = a.faces[3 * face], i1 = a.faces[3 * face + 1], i2 = a.faces[3 * face + 2];
+      V3 A = xform(sM, V3{a.verts[3 * i0], a.verts[3 * i0 + 1], a.verts[3 * i0 + 2]});
+      V3 B = xform(sM, V3{a.verts[3 * i1], a.verts[3 * i1 + 1], a.verts[3 * i1 + 2]});
+      V3 C = xform(sM, V3{a.verts[3 * i2], a.verts[3 * i2 + 1], a.verts[3 * i2 + 2]});
+      Setup s;
+      if (!make_setup(A, B, C, s)) continue;
+      // bounding sphere of the triangle around its centroid
+      const float gx = (A.x + B.x + C.x) * (1.0f / 3.0f), gy = (A.y + B.y + C.y) * (1.0f / 3.0f),
+                  gz = (A.z + B.z + C.z) * (1.0f / 3.0f);
+      auto d2 = [&](V3 P) { return (P.x - gx) * (P.x - gx) + (P.y - gy) * (P.y - gy) + (P.z - gz) * (P.z - gz); };
+      const float rr = sqrtf(fmaxf(d2(A), fmaxf(d2(B), d2(C)))) * 1.0001f + 1e-7f;
+      if (grid_lower_bound(a.grid, gx, gy, gz) > rr) continue;
+      int x0, y0, x1, y1;
+      if (!tri_bbox(A, B, C, x0, y0, x1, y1)) continue;
+      s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+      s.tri = (uint32_t)face;
+      s.orig = (uint32_t)a.face_orig[face];
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < a.kmax) out[slot] = s;
+      atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int n = s_count;
+    a.counts[f] = min(n, a.kmax);
+    if (n > a.kmax || s_ncl > GEOM_MAX_CL) atomicExch(a.overflow, 1);
+    if (n > 0) {
+      a.bbox[4 * f + 0] = s_bb[0]; a.bbox[4 * f + 1] = s_bb[1];
+      a.bbox[4 * f + 2] = s_bb[2]; a.bbox[4 * f + 3] = s_bb[3];
+      a.worklist[atomicAdd(a.work_n, 1)] = f;
+    }
+  }
+}
+
+// ---- K2f: fill -----------------------------------------------------------------------------
+struct FillArgs {
+  const uint8_t* bg_real;    // (n_bg, TH, TW, 3)
+  const int32_t* bg_id;      // (F) index into bg_real
+  const float* obs_empty;    // (OBS_H*OBS_W)
+  const int32_t* counts;     // (F) -1 => frame not updated
+  uint8_t* color;            // (F, TH, TW, 3) or null
+  float* gel_depth;          // (F, TH, TW) or null
+  float* obs;                // frame f at obs + f*obs_stride, (OBS_H*OBS_W) f32
+  int64_t obs_stride;
+  int n_frames;
+};
+constexpr int FILL_BLOCK = 256;
+constexpr int FILL_PARTS = 4;  // CTAs per frame
+
+__global__ void __launch_bounds__(FILL_BLOCK) tac_fill(FillArgs a) {
+  const int f = blockIdx.x / FILL_PARTS, part = blockIdx.x % FILL_PARTS;
+  if (a.counts[f] < 0) return;
+  const int tid = threadIdx.x;
+  if (a.color) {
+    constexpr int NV = TW * TH * 3 / 16;  // 9408 uint4
+    const uint4* src = reinterpret_cast<const uint4*>(a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3);
+    uint4* dst = reinterpret_cast<uint4*>(a.color + (size_t)f * TW * TH * 3);
+    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) __stcs(dst + i, __ldg(src + i));
+  }
+  if (a.gel_depth) {
+    constexpr int NV = TW * TH * 4 / 16;  // 12544 uint4
+    uint4* dst = reinterpret_cast<uint4*>(a.gel_depth + (size_t)f * TW * TH);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) __stcs(dst + i, z);
+  }
+  {
+    constexpr int NV = OBS_W * OBS_H * 4 / 16;  // 512 float4
+    const float4* src = reinterpret_cast<const float4*>(a.obs_empty);
+    float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)f * a.obs_stride);
+    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) dst[i] = __ldg(src + i);
+  }
+}
+
+// ---- contact frames ----------------------------------------------------------------------
+struct ContactArgs {
+  const float* M;            // (F,12)
+  const Setup* setups;
+  const int32_t* counts;
+  const int32_t* bbox;
+  const int32_t* worklist;
+  const int32_t* work_n;
+  int32_t* cursor;           // (1) work-stealing cursor, zeroed by the launcher
+  const float* verts;
+  const float* vnorm;
+  const int32_t* faces;
+  const float* depth0;       // (TH,TW)
+  const uint8_t* bg_sim;     // (TH,TW,3)
+  const uint8_t* bg_real;
+  const int32_t* bg_id;
+  uint8_t* color;            // (F,TH,TW,3)  required
+  float* gel_depth;          // (F,TH,TW)    required
+  float* obs;
+  int64_t obs_stride;
+  int kmax;
+};
+constexpr int CT_BLOCK = 256;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
+  __shared__ unsigned long long s_z[REG * REG];   // depth<<32 | orig<<12 | slot
+  __shared__ float s_diff[REG * REG * 3];         // (c - bg_sim) * scale
+  __shared__ float s_h[REG * TILE * 3];           // horizontal blur
+  __shared__ float sM[12];
+  __shared__ int s_frame;
+  const int tid = threadIdx.x;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      const int w = atomicAdd(a.cursor, 1);
+      s_frame = (w < *a.work_n) ? a.worklist[w] : -1;
+    }
+    __syncthreads();
+    const int f = s_frame;
+    if (f < 0) return;
+    if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
+    const int K = a.counts[f];
+    const Setup* list = a.setups + (size_t)f * a.kmax;
+    // dirty window: triangle bbox dilated by the blur radius
+    const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
+    const int wx1 = min(a.bbox[4 * f + 2] + HALO, TW - 1), wy1 = min(a.bbox[4 * f + 3] + HALO, TH - 1);
+    const uint8_t* bgr = a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3;
+    uint8_t* col = a.color + (size_t)f * TW * TH * 3;
+    float* gdep = a.gel_depth + (size_t)f * TW * TH;
+    __syncthreads();
+
+    for (int ty = wy0; ty <= wy1; ty += TILE)
+      for (int tx = wx0; tx <= wx1; tx += TILE) {
+        // region = tile + halo, in image coordinates [rx0, rx0+REG) x [ry0, ry0+REG)
+        const int rx0 = tx - HALO, ry0 = ty - HALO;
+        for (int i = tid; i < REG * REG; i += CT_BLOCK) s_z[i] = ZEMPTY;
+        __syncthreads();
+        // --- raster: one thread per triangle, pixels of bbox ∩ region
+        for (int k = tid; k < K; k += CT_BLOCK) {
+          const Setup s = list[k];
+          const int bx0 = max((int)(s.bbox & 255u), max(rx0, 0)), by0 = max((int)((s.bbox >> 8) & 255u), max(ry0, 0));
+          const int bx1 = min((int)((s.bbox >> 16) & 255u), min(rx0 + REG - 1, TW - 1));
+          const int by1 = min((int)(s.bbox >> 24), min(ry0 + REG - 1, TH - 1));
+          for (int py = by0; py <= by1; ++py)
+            for (int px = bx0; px <= bx1; ++px) {
+              float e1, e2, es;
+              const float t = cover(s, px, py, e1, e2, es);
+              if (t < 0.0f) continue;
+              const float d0 = a.depth0[py * TW + px];
+              if (d0 != 0.0f && !(t < d0)) continue;  // GL_LESS against the gel
+              const unsigned long long key =
+                  ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)s.orig << 12) | (uint32_t)k;
+              unsigned long long* zp = &s_z[(py - ry0) * REG + (px - rx0)];
+              if (key < *zp) atomicMin(zp, key);
+            }
+        }
+        __syncthreads();
+        // --- shade hits, build the scaled difference image (0 where the gel is visible)
+        for (int i = tid; i < REG * REG; i += CT_BLOCK) {
+          const unsigned long long key = s_z[i];
+          float d[3] = {0.f, 0.f, 0.f};
+          const int px = rx0 + i % REG, py = ry0 + i / REG;
+          if (key != ZEMPTY) {
+            const float t = __uint_as_float((uint32_t)(key >> 32));
+            const Setup s = list[(int)(key & 0xfffu)];
+            const float dx = k_dxp[px], dy = k_dyp[py];
+            const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
+            const float es = add(add(e0, e1), e2);
+            const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
+            const float l0 = sub(sub(1.0f, l1), l2);
+            const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
+            float no[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
+            V3 n;
+            n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
+            n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
+            n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
+            n = normalize(n);
+            V3 p{mul(dx, t), mul(dy, t), -t};
+            uint8_t rgb[3];
+            shade(p, n, rgb);
+            const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
+            // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
+            const int lx = px - tx, ly = py - ty;
+            if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE && px <= wx1 && py <= wy1)
+              gdep[py * TW + px] = sub(a.depth0[py * TW + px], t);
+          }
+          s_diff[3 * i] = d[0]; s_diff[3 * i + 1] = d[1]; s_diff[3 * i + 2] = d[2];
+        }
+        __syncthreads();
+        // --- 7-tap horizontal pass (BORDER_REFLECT_101 at the image edge)
+        for (int i = tid; i < REG * TILE; i += CT_BLOCK) {
+          const int ry = i / TILE, lx = i % TILE;
+          const int px = tx + lx, py = ry0 + ry;
+          float acc[3] = {0.f, 0.f, 0.f};
+          if (px < TW && py >= 0 && py < TH) {
+#pragma unroll
+            for (int k = -3; k <= 3; ++k) {
+              const int sx = reflect101(px + k, TW) - rx0;
+              const float w = kc.gauss[k + 3];
+              const float* dp = &s_diff[(ry * REG + sx) * 3];
+              acc[0] = fmaf(w, dp[0], acc[0]); acc[1] = fmaf(w, dp[1], acc[1]); acc[2] = fmaf(w, dp[2], acc[2]);
+            }
+          }
+          s_h[3 * i] = acc[0]; s_h[3 * i + 1] = acc[1]; s_h[3 * i + 2] = acc[2];
+        }
+        __syncthreads();
+        // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8))
+        for (int i = tid; i < TILE * TILE; i += CT_BLOCK) {
+          const int ly = i / TILE, lx = i % TILE;
+          const int px = tx + lx, py = ty + ly;
+          if (px > wx1 || py > wy1) continue;
+          float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = -3; k <= 3; ++k) {
+            const int sy = reflect101(py + k, TH) - ry0;
+            const float w = kc.gauss[k + 3];
+            const float* hp = &s_h[(sy * TILE + lx) * 3];
+            acc[0] = fmaf(w, hp[0], acc[0]); acc[1] = fmaf(w, hp[1], acc[1]); acc[2] = fmaf(w, hp[2], acc[2]);
+          }
+          const size_t o = ((size_t)py * TW + px) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float v = clampf(acc[c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
+            col[o + c] = (uint8_t)v;
+          }
+        }
+        __syncthreads();
+      }
+    // --- obs pixels whose 3.5x3.5 source window meets the dirty window -----------------------
+    // flipud + crop: obs row r reads flipped rows [3.5r, 3.5r+3.5) = original rows 223 - that.
+    {
+      const int fy_lo = TH - 1 - wy1, fy_hi = TH - 1 - wy0;  // dirty rows in flipped coordinates
+      const int oy0 = max((2 * fy_lo) / 7 - 1, 0), oy1 = min((2 * fy_hi) / 7 + 1, OBS_H - 1);
+      const int ox0 = max((2 * wx0) / 7 - 1, 0), ox1 = min((2 * wx1) / 7 + 1, OBS_W - 1);
+      const int nw = ox1 - ox0 + 1, nh = oy1 - oy0 + 1;
+      float* ob = a.obs + (size_t)f * a.obs_stride;
+      for (int i = tid; i < nw * nh; i += CT_BLOCK) {
+        const int oy = oy0 + i / nw, ox = ox0 + i % nw;
+        // cv2 INTER_AREA, scale 3.5: taps for even/odd destination index
+        const int sx0 = (ox >> 1) * 7 + ((ox & 1) ? 3 : 0), sy0 = (oy >> 1) * 7 + ((oy & 1) ? 3 : 0);
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int j = 0; j < 4; ++j) {
+          const float wy = (oy & 1) ? (j == 0 ? kc.area_w[1] : kc.area_w[0]) : (j == 3 ? kc.area_w[1] : kc.area_w[0]);
+          const int fy = sy0 + j;           // flipped row
+          const int py = TH - 1 - fy;       // original row
+          double racc[3] = {0.0, 0.0, 0.0};
+          for (int k = 0; k < 4; ++k) {
+            const float wx = (ox & 1) ? (k == 0 ? kc.area_w[1] : kc.area_w[0]) : (k == 3 ? kc.area_w[1] : kc.area_w[0]);
+            const int px = sx0 + k;
+            const int ddx = px - TW / 2, ddy = py - TH / 2;
+            const double m = (ddx * ddx + ddy * ddy <= (TW / 2) * (TW / 2)) ? 1.0 : 0.0;  // circle_mask
+            const size_t o = ((size_t)py * TW + px) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const double v = ((double)((int)col[o + c] - (int)bgr[o + c]) / 255.0 + 0.5) * m;  // remove_bg * mask
+              racc[c] += v * (double)wx;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] += racc[c] * (double)wy;
+        }
+        // cvtColor(float32, BGR2GRAY) applied to an RGB-ordered array
+        const float g = 0.114f * (float)acc[0] + 0.587f * (float)acc[1] + 0.299f * (float)acc[2];
+        ob[oy * OBS_W + ox] = g;
+      }
+    }
+  }
+}
+
+// ---- standalone obs kernel (K3) for externally produced color images ------------------------
+__global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t* __restrict__ bg_real,
+                               const int32_t* __restrict__ bg_id, float* __restrict__ obs, int64_t obs_stride,
+                               int n_frames) {
+  const int f = blockIdx.x;
+  const uint8_t* col = color + (size_t)f * TW * TH * 3;
+  const uint8_t* bgr = bg_real + (size_t)bg_id[f] * TW * TH * 3;
+  float* ob = obs + (size_t)f * obs_stride;
+  for (int i = threadIdx.x; i < OBS_W * OBS_H; i += blockDim.x) {
+    const int oy = i / OBS_W, ox = i % OBS_W;
+    const int sx0 = (ox >> 1) * 7 + ((ox & 1) ? 3 : 0), sy0 = (oy >> 1) * 7 + ((oy & 1) ? 3 : 0);
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 4; ++j) {
+      const float wy = (oy & 1) ? (j == 0 ? kc.area_w[1] : kc.area_w[0]) : (j == 3 ? kc.area_w[1] : kc.area_w[0]);
+      const int py = TH - 1 - (sy0 + j);
+      double racc[3] = {0.0, 0.0, 0.0};
+      for (int k = 0; k < 4; ++k) {
+        const float wx = (ox & 1) ? (k == 0 ? kc.area_w[1] : kc.area_w[0]) : (k == 3 ? kc.area_w[1] : kc.area_w[0]);
+        const int px = sx0 + k;
+        const int ddx = px - TW / 2, ddy = py - TH / 2;
+        const double m = (ddx * ddx + ddy * ddy <= (TW / 2) * (TW / 2)) ? 1.0 : 0.0;
+        const size_t o = ((size_t)py * TW + px) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          racc[c] += (((double)((int)col[o + c] - (int)bgr[o + c]) / 255.0 + 0.5) * m) * (double)wx;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += racc[c] * (double)wy;
+    }
+    ob[i] = 0.114f * (float)acc[0] + 0.587f * (float)acc[1] + 0.299f * (float)acc[2];
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
+  IGI_REQUIRE(p != nullptr, "igi_tactile_set_sensor: null params");
+  IGI_REQUIRE(p->width == TW && p->height == TH, "igi_tactile_set_sensor: only 224x224 is built");
+  IGI_REQUIRE(p->n_lights >= 0 && p->n_lights <= MAX_LIGHTS, "igi_tactile_set_sensor: at most 8 lights");
+  IGI_REQUIRE(p->blur_ksize == 7, "igi_tactile_set_sensor: blur kernel size must be 7");
+  TacConst c{};
+  c.znear = p->znear;
+  c.n_lights = p->n_lights;
+  for (int i = 0; i < p->n_lights; ++i) {
+    for (int k = 0; k < 3; ++k) {
+      c.light_pos[i][k] = p->light_pos[3 * i + k];
+      c.light_dir[i][k] = p->light_dir[3 * i + k];
+      c.light_col[i][k] = p->light_col[3 * i + k];
+    }
+    c.light_int[i] = p->light_int[i];
+    c.light_las[i] = p->light_las[i];
+    c.light_lao[i] = p->light_lao[i];
+  }
+  c.inverse_square = p->inverse_square;
+  for (int k = 0; k < 3; ++k) c.base[k] = p->base_color[k];
+  c.metallic = p->metallic;
+  c.roughness = p->roughness;
+  for (int k = 0; k < 9; ++k) c.cam_R[k] = p->cam_R[k];
+  for (int k = 0; k < 3; ++k) c.cam_p[k] = p->cam_p[k];
+  c.gel_camx = (float)p->cam_p[0];
+  c.max_force = p->max_force;
+  c.max_deformation = p->max_deformation;
+  c.calib_scale = p->calib_scale;
+  c.clip_lo = p->clip_lo;
+  c.clip_hi = p->clip_hi;
+  for (int k = 0; k < 7; ++k) c.gauss[k] = p->gauss[k];
+  for (int k = 0; k < 3; ++k) { c.grid_org[k] = p->grid_org[k]; c.grid_n[k] = p->grid_n[k]; }
+  c.grid_h = p->grid_h;
+  c.grid_slack = p->grid_slack;
+  c.depth0_max = p->depth0_max;
+  c.area_w[0] = p->area_w_full;
+  c.area_w[1] = p->area_w_half;
+  IGI_CUDA(cudaMemcpyToSymbol(kc, &c, sizeof(c)));
+  IGI_CUDA(cudaMemcpyToSymbol(k_dxp, p->dxp, sizeof(float) * TW));
+  IGI_CUDA(cudaMemcpyToSymbol(k_dyp, p->dyp, sizeof(float) * TH));
+  return IGI_OK;
+}
+
+extern "C" int igi_tactile_gel_precompute(const float* gel_tris, int n_tris, uint64_t* scratch_zbuf,
+                                          float* depth0, uint8_t* bg_sim, void* stream) {
+  IGI_REQUIRE(gel_tris && scratch_zbuf && depth0 && bg_sim && n_tris > 0, "igi_tactile_gel_precompute: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  IGI_CUDA(cudaMemsetAsync(scratch_zbuf, 0xff, sizeof(uint64_t) * TW * TH, s));
+  tac_gel_raster<<<(n_tris + 127) / 128, 128, 0, s>>>(gel_tris, n_tris, (unsigned long long*)scratch_zbuf);
+  IGI_CHECK_LAUNCH("tac_gel_raster");
+  tac_gel_shade<<<(TW * TH + 255) / 256, 256, 0, s>>>(gel_tris, (const unsigned long long*)scratch_zbuf, depth0, bg_sim);
+  IGI_CHECK_LAUNCH("tac_gel_shade");
+  return IGI_OK;
+}
+
+extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileStatic* st, const IgiTactileFrames* fr,
+                                  const IgiTactileScratch* sc, const IgiTactileOut* out, void* stream) {
+  IGI_REQUIRE(m && st && fr && sc && out, "igi_tactile_render: null struct");
+  IGI_REQUIRE(fr->n_envs >= 0 && fr->sensors_per_env >= 1, "igi_tactile_render: bad frame counts");
+  IGI_REQUIRE(fr->finger_pos && fr->finger_quat && fr->plug_pos && fr->plug_quat && fr->mesh_id && fr->bg_id,
+              "igi_tactile_render: null pose pointer");
+  IGI_REQUIRE(m->verts && m->vnorm && m->faces && m->face_orig && m->meshes && m->clusters,
+              "igi_tactile_render: null mesh pointer");
+  IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid, "igi_tactile_render: null static pointer");
+  IGI_REQUIRE(sc->M && sc->setups && sc->counts && sc->bbox && sc->worklist && sc->counters && sc->kmax > 0 &&
+                  sc->kmax <= 4096,
+              "igi_tactile_render: bad scratch (kmax must be 1..4096)");
+  IGI_REQUIRE(out->obs && out->obs_stride >= OBS_W * OBS_H, "igi_tactile_render: bad obs output");
+  IGI_REQUIRE(out->color && out->gel_depth, "igi_tactile_render: color and gel_depth outputs are required");
+  const int F = fr->n_envs * fr->sensors_per_env;
+  if (F == 0) return IGI_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
+  IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
+  GeomArgs g{};
+  g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
+  g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
+  g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
+  g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid;
+  g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
+  g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
+  g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
+  tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
+  IGI_CHECK_LAUNCH("tac_geom");
+  FillArgs fa{};
+  fa.bg_real = st->bg_real; fa.bg_id = fr->bg_id; fa.obs_empty = st->obs_empty; fa.counts = sc->counts;
+  fa.color = out->color; fa.gel_depth = out->gel_depth; fa.obs = out->obs; fa.obs_stride = out->obs_stride;
+  fa.n_frames = F;
+  tac_fill<<<F * FILL_PARTS, FILL_BLOCK, 0, s>>>(fa);
+  IGI_CHECK_LAUNCH("tac_fill");
+  ContactArgs ca{};
+  ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.counts = sc->counts; ca.bbox = sc->bbox;
+  ca.worklist = sc->worklist; ca.work_n = sc->counters; ca.cursor = sc->counters + 1;
+  ca.verts = m->verts; ca.vnorm = m->vnorm; ca.faces = m->faces;
+  ca.depth0 = st->depth0; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
+  ca.color = out->color; ca.gel_depth = out->gel_depth; ca.obs = out->obs; ca.obs_stride = out->obs_stride;
+  ca.kmax = sc->kmax;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = min(F, sms * 4);
+  tac_contact<<<grid, CT_BLOCK, 0, s>>>(ca);
+  IGI_CHECK_LAUNCH("tac_contact");
+  return IGI_OK;
+}
+
+extern "C" int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames,
+                               float* obs, int64_t obs_stride, void* stream) {
+  IGI_REQUIRE(color && bg_real && bg_id && obs && n_frames >= 0 && obs_stride >= OBS_W * OBS_H, "igi_tactile_obs: bad args");
+  if (n_frames == 0) return IGI_OK;
+  tac_obs_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(color, bg_real, bg_id, obs, obs_stride, n_frames);
+  IGI_CHECK_LAUNCH("tac_obs_kernel");
+  return IGI_OK;
+}

@@ -226,3 +226,85 @@ def scene_poses(n_envs, seed=0, assets=None, global_env_offset=0):
         plug_pos, plug_quat, socket_pos = pp[gid], pq[gid], sp[gid]
     del rng
     return plug_pos, plug_quat, socket_pos
+
+
+# ---------------------------------------------------------------------------
+# tactile poses
+# ---------------------------------------------------------------------------
+GEL_OUTER_R = 0.0140     # outer wall radius of the allsight dome (x,y scaled mesh)
+SENSOR_MID_X = 0.020     # sensor mid-length along its own +x axis
+PLUG_LENGTH = 0.0762
+
+
+def _support_radius(verts, h, phi, band=0.004):
+    """Plug cross-section support distance in direction phi near height h (plug frame)."""
+    sel = np.abs(verts[:, 2] - h) < band
+    v = verts[sel] if sel.any() else verts
+    return float((v[:, 0] * math.cos(phi) + v[:, 1] * math.sin(phi)).max())
+
+
+def _axis_angle(axis, ang):
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + math.sin(ang) * K + (1 - math.cos(ang)) * (K @ K)
+
+
+def tactile_poses(n_envs, assets, seed=0, global_env_offset=0, contact_mix=(0.5, 0.25, 0.25)):
+    """Seeded fingertip / plug poses for N envs x 3 fingertip sensors.
+
+    Per env (global id g): plug mesh g % 7, plug pose from the grasp table; per finger k a
+    sensor whose axis (+x, camera looks along it) is anti-parallel to the plug axis, tilted
+    U(0,40) deg towards the plug, rolled U(0,2pi), its mid-length on a ring at 0.9*plug length,
+    azimuth k*120 + U(-10,10) deg, with the plug surface penetrating the gel's outer wall by
+    delta: `contact_mix` = fractions of (deep U(3,6) mm, grazing U(0,3) mm, none U(-3,0) mm).
+    Returns dict of f32 arrays: finger_pos (N,3,3), finger_quat (N,3,4 xyzw), plug_pos (N,3),
+    plug_quat (N,4), mesh_id (N) i32, bg_id (N,3) i32 in 12..19, delta (N,3).
+    """
+    out = dict(finger_pos=np.empty((n_envs, 3, 3), np.float32), finger_quat=np.empty((n_envs, 3, 4), np.float32),
+               plug_pos=np.empty((n_envs, 3), np.float32), plug_quat=np.empty((n_envs, 4), np.float32),
+               mesh_id=np.empty(n_envs, np.int32), bg_id=np.empty((n_envs, 3), np.int32),
+               delta=np.empty((n_envs, 3), np.float32))
+    n_pegs = len(assets["peg_names"])
+    verts = [np.asarray(assets[f"peg_{i}_v"], dtype=np.float64) for i in range(n_pegs)]
+    h = 0.9 * PLUG_LENGTH
+    for k in range(n_envs):
+        g = global_env_offset + k
+        rng = np.random.default_rng([seed, g])          # counter-based: independent of the sharding
+        mid = g % n_pegs
+        row = (g // n_pegs) % len(assets[f"grasp_{mid}_plug_pos"])
+        ppos = np.asarray(assets[f"grasp_{mid}_plug_pos"][row], dtype=np.float64)
+        pquat = np.asarray(assets[f"grasp_{mid}_plug_quat"][row], dtype=np.float64)
+        Rp = quat_to_matrix(pquat)
+        out["plug_pos"][k] = ppos
+        out["plug_quat"][k] = pquat / np.linalg.norm(pquat)
+        out["mesh_id"][k] = mid
+        for f in range(3):
+            phi = math.radians(120.0 * f + rng.uniform(-10, 10))
+            u = rng.random()
+            if u < contact_mix[0]:
+                delta = rng.uniform(0.003, 0.006)
+            elif u < contact_mix[0] + contact_mix[1]:
+                delta = rng.uniform(0.0, 0.003)
+            else:
+                delta = rng.uniform(-0.003, 0.0)
+            tilt = math.radians(rng.uniform(0, 40))
+            roll = rng.uniform(0, 2 * math.pi)
+            radial = np.array([math.cos(phi), math.sin(phi), 0.0])
+            tang = np.array([-math.sin(phi), math.cos(phi), 0.0])
+            rho = _support_radius(verts[mid], h, phi) + GEL_OUTER_R - delta
+            p_mid = radial * rho + np.array([0, 0, h])
+            # sensor axes in the plug frame: x_s = -z tilted towards the plug axis about the tangent
+            x_s = _axis_angle(tang, -tilt) @ np.array([0.0, 0.0, -1.0])
+            if x_s @ radial > 0:                          # make sure the tip leans towards the plug
+                x_s = _axis_angle(tang, tilt) @ np.array([0.0, 0.0, -1.0])
+            y0 = tang
+            z0 = np.cross(x_s, y0)
+            Rs = np.stack([x_s, y0, z0], axis=1) @ _axis_angle([1, 0, 0], roll)
+            origin = p_mid - SENSOR_MID_X * x_s
+            Rw = Rp @ Rs
+            out["finger_pos"][k, f] = ppos + Rp @ origin
+            out["finger_quat"][k, f] = matrix_to_quat(Rw)
+            out["bg_id"][k, f] = 12 + int(rng.integers(0, 8))
+            out["delta"][k, f] = delta
+    return out

@@ -1,0 +1,72 @@
+"""CPU: tactile oracle self-checks (the cv2 / scipy stages run the real libraries; the raster
+stage is the unpinned restatement in oracle/raster.c)."""
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from isaacgyminsertion_b200 import synthetic
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+@pytest.fixture(scope="module")
+def model():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    from oracle import tactile as ot
+    return ot.SensorModel()
+
+
+def test_gel_background(model):
+    assert (model.depth0 > 0).all(), "gel covers the whole image (SURVEY 9)"
+    assert 0.0245 < model.depth0.max() < 0.0255            # dome tip, SURVEY 9: 24.95 mm
+    assert abs(model.depth0[112, 112] - model.depth0.max()) < 1e-3
+    assert model.bg_sim.min() > 20 and model.bg_sim.max() < 120, "light model must not saturate"
+
+
+def test_no_contact_invariant(model):
+    """Where the peg is not in front of the gel: color == bg_real, gel_depth == 0, obs == 0.5*mask resized."""
+    from oracle import tactile as ot
+    h = ot.OracleAllSight(model, 0, 15)
+    far = np.eye(4)
+    far[:3, 3] = [1.0, 1.0, 1.0]
+    h.update_pose_given_sim_pose(np.eye(4), far)
+    color, gd = h.render(far, 70)
+    assert np.array_equal(color, model.bg_real[3]) and not gd.any()
+    obs = ot.tactile_obs(color, h.bg_img, h.mask)
+    m = cv2.resize(np.flipud(0.5 * h.mask.astype(np.float64))[:112], (64, 32), interpolation=cv2.INTER_AREA)
+    want = cv2.cvtColor(m.astype(np.float32), cv2.COLOR_BGR2GRAY).flatten()
+    assert np.array_equal(obs, want)
+    assert abs(obs.max() - 0.5) < 1e-6 and obs.min() == 0.0
+
+
+def test_contact_mix_of_synthetic_poses(model):
+    from oracle import tactile as ot
+    P = synthetic.tactile_poses(21, model.assets, seed=1)
+    obj_tf = ot.xyzquat_to_tf_numpy(np.concatenate([P["plug_pos"], P["plug_quat"]], 1))
+    visible = 0
+    for e in range(21):
+        for n in range(3):
+            h = ot.OracleAllSight(model, int(P["mesh_id"][e]), int(P["bg_id"][e, n]))
+            ftf = ot.xyzquat_to_tf_numpy(np.concatenate([P["finger_pos"][e, n], P["finger_quat"][e, n]]))[0]
+            h.update_pose_given_sim_pose(ftf, obj_tf[e])
+            color, gd = h.render(obj_tf[e], 70)
+            assert (gd >= 0).all()
+            vis = (gd > 0).mean() > 0.01
+            visible += vis
+            if vis:
+                assert not np.array_equal(color, h.bg_img)
+    assert 0.3 <= visible / 63 <= 0.8, f"contact mix {visible}/63"
+
+
+def test_force_shift_moves_peg_towards_camera(model):
+    tf = np.eye(4)
+    obj = np.eye(4)
+    obj[:3, 3] = [0.05, 0.0, 0.0]
+    M0 = model.object_in_camera(tf, obj, 0.0)
+    M1 = model.object_in_camera(tf, obj, 70.0)     # clipped to 10 -> full 10 mm shift
+    d0 = np.linalg.norm(M0[:, 3])
+    d1 = np.linalg.norm(M1[:, 3])
+    assert abs((d0 - d1) - 0.01) < 1e-5

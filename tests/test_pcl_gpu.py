@@ -76,7 +76,11 @@ def test_get_ptd_cuda_and_convert(golden, cam):
     gym, gen = cam
     from isaacgyminsertion_b200.pcl_utils import PointCloudGenerator
     depth = torch.from_numpy(golden["depth"]).cuda()
-    lst = gen.get_ptd_cuda(depth[:3], env_ids=[0, 1, 2], filter_func=None)
+    from isaacgyminsertion_b200.pcl_utils import CameraPointCloud
+    raw_gen = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props, sample_num=400,
+                               filter_func=None, pt_in_local=True, graphics_device="cuda:0",
+                               compute_device="cuda:0")
+    lst = raw_gen.get_ptd_cuda(depth[:3], env_ids=[0, 1, 2])
     np.testing.assert_allclose(lst[0].cpu().numpy(), golden["unfiltered0"], rtol=1e-5, atol=_tol(gym))
     o = gym.get_env_origin(0)
     e2g = np.identity(4)

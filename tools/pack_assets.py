@@ -39,57 +39,8 @@ SUBASSEMBLIES = [
 ]
 
 
-def load_obj(path):
-    """All-triangle OBJ -> (V f64 (nv,3), F i64 (nf,3)); ignores vn/vt."""
-    vs, fs = [], []
-    with open(path) as fh:
-        for line in fh:
-            if line.startswith("v "):
-                p = line.split()
-                vs.append((float(p[1]), float(p[2]), float(p[3])))
-            elif line.startswith("f "):
-                p = line.split()[1:]
-                idx = [int(t.split("/")[0]) for t in p]
-                assert len(idx) == 3, f"non-triangle face in {path}"
-                fs.append(idx)
-    V = np.asarray(vs, dtype=np.float64)
-    F = np.asarray(fs, dtype=np.int64)
-    F = np.where(F > 0, F - 1, F + len(V))
-    return V, F
-
-
-def merge_vertices(V, F, digits=8):
-    """Merge vertices on rounded position (trimesh merge_vertices default, tol 1e-8)."""
-    key = np.round(V, digits)
-    _, first, inverse = np.unique(key, axis=0, return_index=True, return_inverse=True)
-    # keep first-occurrence order so face indices stay in file order
-    order = np.argsort(first)
-    rank = np.empty_like(order)
-    rank[order] = np.arange(len(order))
-    Vm = V[first[order]]
-    Fm = rank[inverse.reshape(-1)][F]
-    return Vm, Fm
-
-
-def angle_weighted_normals(V, F):
-    tri = V[F]
-    e0 = tri[:, 1] - tri[:, 0]
-    e1 = tri[:, 2] - tri[:, 0]
-    fn = np.cross(e0, e1)
-    ln = np.linalg.norm(fn, axis=1, keepdims=True)
-    fn = np.where(ln > 0, fn / np.maximum(ln, 1e-300), 0.0)
-    vn = np.zeros_like(V)
-    for k in range(3):
-        a = tri[:, (k + 1) % 3] - tri[:, k]
-        b = tri[:, (k + 2) % 3] - tri[:, k]
-        na = np.linalg.norm(a, axis=1)
-        nb = np.linalg.norm(b, axis=1)
-        c = np.einsum("ij,ij->i", a, b) / np.maximum(na * nb, 1e-300)
-        ang = np.arccos(np.clip(c, -1.0, 1.0))
-        np.add.at(vn, F[:, k], fn * ang[:, None])
-    ln = np.linalg.norm(vn, axis=1, keepdims=True)
-    vn = np.where(ln > 0, vn / np.maximum(ln, 1e-300), 0.0)
-    return vn
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from isaacgyminsertion_b200.assets import load_obj, merge_vertices, angle_weighted_normals  # noqa: E402
 
 
 def main():
