@@ -154,6 +154,8 @@ typedef struct IgiTactileFrames {
   const uint8_t* update;        /* (n_envs) update_freq & update_delay or NULL (all) (task :523) */
   const int32_t* mesh_id;       /* (n_envs) */
   const int32_t* bg_id;         /* (n_envs*S) index into bg_real */
+  int32_t stage_mask;           /* 0 = whole pipeline; else bit0 geometry, bit1 fill, bit2 contact
+                                   (profiling: later stages reuse the scratch of an earlier full run) */
 } IgiTactileFrames;
 
 typedef struct IgiTactileScratch {
@@ -169,8 +171,10 @@ typedef struct IgiTactileScratch {
 typedef struct IgiTactileOut {
   uint8_t* color;               /* (F,H,W,3) calibrated tactile image, AllSightRenderer.render()[0] */
   float* gel_depth;             /* (F,H,W)   depth0 - depth,           AllSightRenderer.render()[1] */
-  float* obs;                   /* frame f at obs + f*obs_stride: (2048) f32 = tactile_imgs[e,n] (task :574) */
-  int64_t obs_stride;
+  float* obs;                   /* frame (e,n) at obs + e*obs_env_stride + n*obs_sensor_stride:
+                                   (2048) f32 = tactile_imgs[e,n] (task :574); strides in floats, % 4 == 0,
+                                   so the rows can live inside a packed [tactile|pcl] send buffer */
+  int64_t obs_env_stride, obs_sensor_stride;
 } IgiTactileOut;
 
 /* Upload sensor constants.  Replaces Renderer.__init__/_init_camera/_init_light

@@ -62,7 +62,8 @@ class IgiTactileFrames(_c.Structure):
                 ("finger_pos", _c.c_void_p), ("finger_quat", _c.c_void_p),
                 ("plug_pos", _c.c_void_p), ("plug_quat", _c.c_void_p),
                 ("force", _c.c_void_p), ("force_const", _c.c_float),
-                ("update", _c.c_void_p), ("mesh_id", _c.c_void_p), ("bg_id", _c.c_void_p)]
+                ("update", _c.c_void_p), ("mesh_id", _c.c_void_p), ("bg_id", _c.c_void_p),
+                ("stage_mask", _c.c_int32)]
 
 
 class IgiTactileScratch(_c.Structure):
@@ -72,7 +73,7 @@ class IgiTactileScratch(_c.Structure):
 
 class IgiTactileOut(_c.Structure):
     _fields_ = [("color", _c.c_void_p), ("gel_depth", _c.c_void_p), ("obs", _c.c_void_p),
-                ("obs_stride", _c.c_int64)]
+                ("obs_env_stride", _c.c_int64), ("obs_sensor_stride", _c.c_int64)]
 
 
 def euler2matrix(angles=(0, 0, 0), translation=(0, 0, 0), xyz="xyz", degrees=False):
@@ -331,16 +332,17 @@ class BatchedAllSight:
 
     # ------------------------------------------------------------------------------------
     @torch.no_grad()
-    def render(self, finger_pos, finger_quat, plug_pos, plug_quat, force=None, update=None, obs_out=None):
+    def render(self, finger_pos, finger_quat, plug_pos, plug_quat, force=None, update=None, obs_out=None,
+               stage_mask=0):
         """One batched pass.  finger_pos (N,S,3), finger_quat (N,S,4 xyzw), plug_pos (N,3),
         plug_quat (N,4) f32 CUDA tensors; force: None (=70, factory_task_insertion.py:535),
         scalar, or (N,S) tensor; update: None or (N,) bool/uint8 (task :523).
         Fills self.color / self.gel_depth / obs (default self.obs, shape (N,S,2048)); frames of
         envs whose update flag is off are left untouched."""
         obs = self.obs if obs_out is None else obs_out
-        if obs.shape != (self.N, self.S, OBS_LEN) or obs.stride(-1) != 1 or obs.stride(1) != OBS_LEN \
-                or obs.stride(0) != self.S * OBS_LEN:
-            raise RuntimeError("obs_out must be a contiguous (N,S,2048) f32 CUDA tensor")
+        if obs.shape != (self.N, self.S, OBS_LEN) or obs.stride(-1) != 1 or obs.dtype != torch.float32 \
+                or not obs.is_cuda or obs.data_ptr() % 16 != 0:
+            raise RuntimeError("obs_out must be a (N,S,2048) f32 CUDA tensor with unit inner stride")
         fr = IgiTactileFrames()
         fr.n_envs, fr.sensors_per_env = self.N, self.S
         fp = finger_pos.reshape(self.F, 3)
@@ -367,9 +369,10 @@ class BatchedAllSight:
         else:
             fr.update = None
         fr.mesh_id, fr.bg_id = self.mesh_id.data_ptr(), self.bg_index.data_ptr()
+        fr.stage_mask = int(stage_mask)
         out = IgiTactileOut()
         out.color, out.gel_depth, out.obs = self.color.data_ptr(), self.gel_depth.data_ptr(), obs.data_ptr()
-        out.obs_stride = OBS_LEN
+        out.obs_env_stride, out.obs_sensor_stride = obs.stride(0), obs.stride(1)
         rc = self.lib.igi_tactile_render(_c.byref(self._m), _c.byref(self._st), _c.byref(fr), _c.byref(self._sc),
                                          _c.byref(out), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_tactile_render")

@@ -402,8 +402,9 @@ struct FillArgs {
   const int32_t* counts;     // (F) -1 => frame not updated
   uint8_t* color;            // (F, TH, TW, 3) or null
   float* gel_depth;          // (F, TH, TW) or null
-  float* obs;                // frame f at obs + f*obs_stride, (OBS_H*OBS_W) f32
-  int64_t obs_stride;
+  float* obs;                // frame (e,n) at obs + e*obs_env_stride + n*obs_sensor_stride
+  int64_t obs_env_stride, obs_sensor_stride;
+  int sensors_per_env;
   int n_frames;
 };
 constexpr int FILL_BLOCK = 256;
@@ -428,7 +429,8 @@ __global__ void __launch_bounds__(FILL_BLOCK) tac_fill(FillArgs a) {
   {
     constexpr int NV = OBS_W * OBS_H * 4 / 16;  // 512 float4
     const float4* src = reinterpret_cast<const float4*>(a.obs_empty);
-    float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)f * a.obs_stride);
+    float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
+                                            (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride);
     for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) dst[i] = __ldg(src + i);
   }
 }
@@ -452,7 +454,8 @@ struct ContactArgs {
   uint8_t* color;            // (F,TH,TW,3)  required
   float* gel_depth;          // (F,TH,TW)    required
   float* obs;
-  int64_t obs_stride;
+  int64_t obs_env_stride, obs_sensor_stride;
+  int sensors_per_env;
   int kmax;
 };
 constexpr int CT_BLOCK = 256;
@@ -599,7 +602,8 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
       const int oy0 = max((2 * fy_lo) / 7 - 1, 0), oy1 = min((2 * fy_hi) / 7 + 1, OBS_H - 1);
       const int ox0 = max((2 * wx0) / 7 - 1, 0), ox1 = min((2 * wx1) / 7 + 1, OBS_W - 1);
       const int nw = ox1 - ox0 + 1, nh = oy1 - oy0 + 1;
-      float* ob = a.obs + (size_t)f * a.obs_stride;
+      float* ob = a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
+                  (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride;
       for (int i = tid; i < nw * nh; i += CT_BLOCK) {
         const int oy = oy0 + i / nw, ox = ox0 + i % nw;
         // cv2 INTER_AREA, scale 3.5: taps for even/odd destination index
@@ -738,13 +742,18 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   IGI_REQUIRE(sc->M && sc->setups && sc->counts && sc->bbox && sc->worklist && sc->counters && sc->kmax > 0 &&
                   sc->kmax <= 4096,
               "igi_tactile_render: bad scratch (kmax must be 1..4096)");
-  IGI_REQUIRE(out->obs && out->obs_stride >= OBS_W * OBS_H, "igi_tactile_render: bad obs output");
+  IGI_REQUIRE(out->obs && out->obs_sensor_stride >= OBS_W * OBS_H &&
+                  out->obs_env_stride >= out->obs_sensor_stride * fr->sensors_per_env &&
+                  out->obs_env_stride % 4 == 0 && out->obs_sensor_stride % 4 == 0,
+              "igi_tactile_render: bad obs output strides");
   IGI_REQUIRE(out->color && out->gel_depth, "igi_tactile_render: color and gel_depth outputs are required");
   const int F = fr->n_envs * fr->sensors_per_env;
   if (F == 0) return IGI_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const int stages = fr->stage_mask ? fr->stage_mask : 7;
   // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
-  IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
+  if (stages & 1) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
+  else IGI_CUDA(cudaMemsetAsync(sc->counters + 1, 0, sizeof(int32_t), s));
   GeomArgs g{};
   g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
@@ -753,27 +762,37 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
-  tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
-  IGI_CHECK_LAUNCH("tac_geom");
+  if (stages & 1) {
+    tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
+    IGI_CHECK_LAUNCH("tac_geom");
+  }
   FillArgs fa{};
   fa.bg_real = st->bg_real; fa.bg_id = fr->bg_id; fa.obs_empty = st->obs_empty; fa.counts = sc->counts;
-  fa.color = out->color; fa.gel_depth = out->gel_depth; fa.obs = out->obs; fa.obs_stride = out->obs_stride;
+  fa.color = out->color; fa.gel_depth = out->gel_depth; fa.obs = out->obs;
+  fa.obs_env_stride = out->obs_env_stride; fa.obs_sensor_stride = out->obs_sensor_stride;
+  fa.sensors_per_env = fr->sensors_per_env;
   fa.n_frames = F;
-  tac_fill<<<F * FILL_PARTS, FILL_BLOCK, 0, s>>>(fa);
-  IGI_CHECK_LAUNCH("tac_fill");
+  if (stages & 2) {
+    tac_fill<<<F * FILL_PARTS, FILL_BLOCK, 0, s>>>(fa);
+    IGI_CHECK_LAUNCH("tac_fill");
+  }
   ContactArgs ca{};
   ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.counts = sc->counts; ca.bbox = sc->bbox;
   ca.worklist = sc->worklist; ca.work_n = sc->counters; ca.cursor = sc->counters + 1;
   ca.verts = m->verts; ca.vnorm = m->vnorm; ca.faces = m->faces;
   ca.depth0 = st->depth0; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
-  ca.color = out->color; ca.gel_depth = out->gel_depth; ca.obs = out->obs; ca.obs_stride = out->obs_stride;
+  ca.color = out->color; ca.gel_depth = out->gel_depth; ca.obs = out->obs;
+  ca.obs_env_stride = out->obs_env_stride; ca.obs_sensor_stride = out->obs_sensor_stride;
+  ca.sensors_per_env = fr->sensors_per_env;
   ca.kmax = sc->kmax;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = min(F, sms * 4);
-  tac_contact<<<grid, CT_BLOCK, 0, s>>>(ca);
-  IGI_CHECK_LAUNCH("tac_contact");
+  if (stages & 4) {
+    tac_contact<<<grid, CT_BLOCK, 0, s>>>(ca);
+    IGI_CHECK_LAUNCH("tac_contact");
+  }
   return IGI_OK;
 }
 

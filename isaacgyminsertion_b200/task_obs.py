@@ -1,0 +1,189 @@
+"""Observation members of `FactoryTaskInsertionTactile`, batched.
+
+Mirror of the reference task's observation buffers and functions
+(isaacgyminsertion/tasks/factory_tactile/factory_task_insertion.py):
+  buffers                         :273-338   tactile_imgs, tactile_queue, pcl, pcl_queue, seg_buf,
+                                             image_buf, socket_pcl, got_socket
+  update_tactile / _render_tactile :479-583
+  update_external_cam              :896-1056
+  reset bookkeeping                :1753-1777
+  obs_dict assembly                :2126-2144
+Same method names and arguments; IsaacGym state (fingertip / plug poses, camera image
+tensors) is whatever the caller assigns to the attributes the reference reads
+(`left_finger_pos`, ..., `cam_renders`, `seg_renders`), e.g. `synthetic` tensors.
+
+tactile_imgs and pcl are two views of ONE packed row [3*2048 | 2400] per env
+(`obs_packed`), so the multi-GPU all-gather (dist.py) sends the kernels' output buffer
+directly, with no pack step.
+"""
+import numpy as np
+import torch
+from scipy.spatial.transform import Rotation as R
+
+from .allsight_render import BatchedAllSight, OBS_LEN
+from .pcl_utils import CameraPointCloud, filter_pts
+
+TACTILE_FLOATS = 3 * OBS_LEN
+
+
+class PointCloudAugmentations:
+    """factory_utils.py:83-166; only `random_noise` is live (`augment` :157-166)."""
+
+    def __init__(self, num_points=400, sigma=0.001, noise_clip=0.001):
+        self.num_points = num_points
+        self.sigma = sigma
+        self.const_noise = 0.001
+        self.noise_clip = noise_clip
+
+    def random_noise(self, pointcloud_batch, pcl_noise, noise_prob=0.3):
+        B, N, _ = pointcloud_batch.shape
+        pointwise = torch.clamp(torch.randn_like(pointcloud_batch) * self.sigma, -self.noise_clip, self.noise_clip)
+        mask = (torch.rand(B, N, device=pointcloud_batch.device) < noise_prob).unsqueeze(-1).float()
+        pointcloud_batch = pointcloud_batch + pointwise * mask
+        const = torch.clamp(pcl_noise * self.const_noise, -self.noise_clip, self.noise_clip)
+        return pointcloud_batch + const
+
+    def augment(self, pointcloud_batch, angle, axes, pcl_noise, dropout_ratio=0.2):
+        if not pointcloud_batch.shape[0]:
+            return pointcloud_batch
+        return self.random_noise(pointcloud_batch, pcl_noise)
+
+
+class FactoryTaskInsertionTactileObs:
+    def __init__(self, num_envs, gym, mesh_ids, bg_ids=None, device="cuda", num_points=400, num_points_socket=400,
+                 tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=2048,
+                 strict_rng=True, pcl_noise_enabled=False):
+        self.device = torch.device(device)
+        self.num_envs = num_envs
+        self.fingertips = ["finger_1_3", "finger_2_3", "finger_3_3"]   # factory_env_insertion.py:748
+        self.num_points, self.num_points_socket = num_points, num_points_socket
+        self.pcl_floats = (num_points + num_points_socket) * 3
+        self.sampler = sampler
+        self.strict_rng = strict_rng
+        self.pcl_noise_enabled = pcl_noise_enabled   # RNG-defined augmentation
+        dev = self.device
+        N = num_envs
+        # packed observation rows: [tactile (3*2048) | pcl (2400)]
+        self.obs_packed = torch.zeros((N, TACTILE_FLOATS + self.pcl_floats), dtype=torch.float32, device=dev)
+        self.tactile_imgs = self.obs_packed[:, :TACTILE_FLOATS].view(N, 3, OBS_LEN)
+        self.pcl = self.obs_packed[:, TACTILE_FLOATS:]
+        self.tactile_queue = torch.zeros((N, tact_hist_len, 3, OBS_LEN), dtype=torch.float32, device=dev)
+        self.pcl_queue = torch.zeros((N, pcl_hist_len, self.pcl_floats), dtype=torch.float32, device=dev)
+        self.socket_pcl = torch.zeros((N, num_points_socket, 3), dtype=torch.float32, device=dev)
+        self.got_socket = torch.zeros((N, 1), dtype=torch.int32, device=dev)
+        self._socket_pending = True        # host mirror of `not self.got_socket.all()` (no sync)
+        self.pcl_pos_noise = torch.randn(N, 1, 3, device=dev)
+        self.rot_pcl_angle = torch.zeros(N, device=dev)
+        self.rot_axes = torch.zeros(N, dtype=torch.long, device=dev)
+        self.pcl_process = PointCloudAugmentations(num_points=num_points)
+        self.res = [gym.width, gym.height]
+        self.seg_buf = torch.zeros(N, self.res[1] * self.res[0], dtype=torch.int32, device=dev)
+        self.tactile = tactile
+        self.pcl_cam = pcl_cam
+        if tactile:
+            self.tactile_engine = BatchedAllSight(N, mesh_ids, bg_ids, device=dev, kmax=kmax)
+            self.tactile_handles = None    # built lazily by `handles()`
+        if pcl_cam:
+            self.pcl_generator = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props,
+                                                  sample_num=num_points, filter_func=filter_pts, pt_in_local=True,
+                                                  graphics_device=dev, compute_device=dev, sampler=sampler)
+            self._plug_pts = torch.zeros((N, num_points, 3), dtype=torch.float32, device=dev)
+        # state the reference reads from gym tensors
+        z3 = torch.zeros((N, 3), device=dev)
+        q4 = torch.tensor([0, 0, 0, 1.0], device=dev).repeat(N, 1)
+        self.left_finger_pos, self.right_finger_pos, self.middle_finger_pos = z3.clone(), z3.clone(), z3.clone()
+        self.left_finger_quat, self.right_finger_quat, self.middle_finger_quat = q4.clone(), q4.clone(), q4.clone()
+        self.plug_pos, self.plug_quat = z3.clone(), q4.clone()
+        self.finger_normalized_forces = torch.zeros((N, 3), device=dev)
+        self.tactile_wrt_force = False
+        self.cam_renders = None            # (N,H,W) f32 depth  (torch.stack(self.cam_renders) in the reference)
+        self.seg_renders = None            # (N,H,W) i32 segmentation
+
+    # ------------------------------------------------------------------ tactile
+    def handles(self):
+        if self.tactile_handles is None:
+            self.tactile_handles = self.tactile_engine.handles()
+        return self.tactile_handles
+
+    @torch.no_grad()
+    def update_tactile(self, update_freq, update_delay):
+        """factory_task_insertion.py:479-513, poses stay on the device in f32."""
+        fpos = torch.stack((self.left_finger_pos, self.right_finger_pos, self.middle_finger_pos), dim=1).contiguous()
+        fquat = torch.stack((self.left_finger_quat, self.right_finger_quat, self.middle_finger_quat), dim=1).contiguous()
+        update = torch.logical_and(update_freq, update_delay)
+        force = (100 * self.finger_normalized_forces) if self.tactile_wrt_force else None   # :532-535
+        self.tactile_engine.render(fpos, fquat, self.plug_pos.contiguous(), self.plug_quat.contiguous(),
+                                   force=force, update=update, obs_out=self.tactile_imgs)
+        self.tactile_queue[:, 1:] = self.tactile_queue[:, :-1].clone().detach()
+        self.tactile_queue[:, 0, ...] = self.tactile_imgs
+
+    @torch.no_grad()
+    def _render_tactile(self, left_finger_pose, right_finger_pose, middle_finger_pose, object_pose, update_freq,
+                        update_delay):
+        """factory_task_insertion.py:515-583 with its (N,4,4) host matrices."""
+        def pq(T):
+            T = np.asarray(T, dtype=np.float64)
+            return T[:, :3, 3].astype(np.float32), R.from_matrix(T[:, :3, :3]).as_quat().astype(np.float32)
+        ps, qs = zip(*(pq(T) for T in (left_finger_pose, right_finger_pose, middle_finger_pose)))
+        op, oq = pq(object_pose)
+        dev = self.device
+        update = torch.logical_and(torch.as_tensor(update_freq, device=dev), torch.as_tensor(update_delay, device=dev))
+        force = (100 * self.finger_normalized_forces) if self.tactile_wrt_force else None
+        self.tactile_engine.render(torch.from_numpy(np.stack(ps, 1)).to(dev), torch.from_numpy(np.stack(qs, 1)).to(dev),
+                                   torch.from_numpy(op).to(dev), torch.from_numpy(oq).to(dev), force=force,
+                                   update=update, obs_out=self.tactile_imgs)
+
+    # ------------------------------------------------------------------ external camera
+    @torch.no_grad()
+    def update_external_cam(self, update_freq, update_delay, seg_update_delay, seg_noise, pcl_noise):
+        """factory_task_insertion.py:896-1056 (cam_type 'd', seg_cam + pcl_cam, merge_socket_pcl,
+        include_plug_pcl — the shipped student configuration)."""
+        update = torch.logical_and(update_freq, update_delay)
+        update_seg = torch.logical_and(update_freq, seg_update_delay)
+        depth, seg = self.cam_renders, self.seg_renders
+        N = self.num_envs
+        self.seg_buf = torch.where(update_seg[:, None], seg.reshape(N, -1), self.seg_buf)            # :934-940
+        gen = self.pcl_generator
+        box = filter_pts.box
+        compute_socket = self._socket_pending
+        pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3) if compute_socket else (2,), box)     # :956-959,975
+        self._sample(pts, cnt, any_, 0, self.num_points, self._plug_pts)                             # :961-964
+        plug_pts = self._plug_pts
+        noisy = pcl_noise.clone()
+        if self.pcl_noise_enabled:
+            plug_pts = torch.where(noisy[:, None, None], self.pcl_process.augment(
+                plug_pts, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), plug_pts)          # :966-969
+        if compute_socket:                                                                          # :972-989
+            self._sample(pts, cnt, any_, 1, self.num_points_socket, self.socket_pcl)
+            restarted = self.got_socket[:, 0] == 0
+            noisy = noisy | restarted
+            if self.pcl_noise_enabled:
+                self.socket_pcl.copy_(torch.where(noisy[:, None, None], self.pcl_process.augment(
+                    self.socket_pcl, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), self.socket_pcl))
+            self.got_socket[restarted] = 1
+            update = update | restarted
+            self._socket_pending = False
+        merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)                  # :1014-1027
+        self.pcl.copy_(torch.where(update[:, None], merged, self.pcl))
+        self.pcl_queue[:, 1:] = self.pcl_queue[:, :-1].clone().detach()                              # :1046-1048
+        self.pcl_queue[:, 0, ...] = self.pcl
+
+    def _sample(self, pts, cnt, any_, cls, m, out):
+        eng = self.pcl_generator.engine
+        if self.sampler == "fps":
+            eng.sample_fps(pts, cnt, any_, cls, m, out=out)
+        else:
+            eng.sample_reference(pts, cnt, any_, cls, m, out=out, strict_rng=self.strict_rng)
+
+    # ------------------------------------------------------------------ reset / obs
+    def reset_idx(self, env_ids):
+        """Observation part of the reset (factory_task_insertion.py:1753-1777)."""
+        self.tactile_queue[env_ids] = 0
+        self.pcl_queue[env_ids] = 0
+        self.got_socket[env_ids] = 0
+        self._socket_pending = True
+
+    def obs_dict(self, rl_device=None):
+        """factory_task_insertion.py:2126-2144."""
+        dev = rl_device or self.device
+        return {"tactile": self.tactile_queue.clone().to(dev), "pcl": self.pcl_queue.clone().to(dev)}

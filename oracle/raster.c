@@ -144,28 +144,38 @@ static void raster_tri(const OracleCam* c, const float* A, const float* B, const
   cross3(C, A, n1);
   cross3(A, B, n2);
 
-  /* conservative pixel bounding box (need not match the GPU's, only contain the triangle) */
-  int x0 = 0, x1 = c->W - 1, y0 = 0, y1 = c->H - 1;
-  float zA = -A[2], zB = -B[2], zC = -C[2];
-  float zmin = fminf(zA, fminf(zB, zC));
-  if (zmin > 1e-6f) {
+  /* conservative pixel bounding box of the part of the triangle at depth >= znear (what GL
+   * keeps after near-plane clipping); it need not match the GPU's box, only contain it */
+  int x0, x1, y0, y1;
+  {
+    const float zn = c->znear;
+    const float* P[3] = {A, B, C};
+    float Z[3] = {-A[2], -B[2], -C[2]};
+    if (fmaxf(Z[0], fmaxf(Z[1], Z[2])) < zn) return; /* entirely in front of the near plane */
+    float mnx = 1e30f, mxx = -1e30f, mny = 1e30f, mxy = -1e30f;
+    for (int i = 0; i < 3; ++i) {
+      int j = (i + 1) % 3;
+      if (Z[i] >= zn) {
+        float sx = P[i][0] / Z[i], sy = P[i][1] / Z[i];
+        mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+      }
+      if ((Z[i] >= zn) != (Z[j] >= zn)) {
+        float t = (zn - Z[i]) / (Z[j] - Z[i]);
+        float sx = (P[i][0] + t * (P[j][0] - P[i][0])) / zn, sy = (P[i][1] + t * (P[j][1] - P[i][1])) / zn;
+        mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
+      }
+    }
     float sx0 = c->dxp[0], sx1 = c->dxp[c->W - 1];
     float sy0 = c->dyp[0], sy1 = c->dyp[c->H - 1];
-    float ax = A[0] / zA, bx = B[0] / zB, cx = C[0] / zC;
-    float ay = A[1] / zA, by = B[1] / zB, cy = C[1] / zC;
-    float mnx = fminf(ax, fminf(bx, cx)), mxx = fmaxf(ax, fmaxf(bx, cx));
-    float mny = fminf(ay, fminf(by, cy)), mxy = fmaxf(ay, fmaxf(by, cy));
     float kx = (float)(c->W - 1) / (sx1 - sx0);
     float ky = (float)(c->H - 1) / (sy1 - sy0); /* negative: rows grow downwards */
     float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
     float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
-    if (fx1 < -1.0f || fy1 < -1.0f || fx0 > (float)c->W || fy0 > (float)c->H) return;
+    if (fx1 < -2.0f || fy1 < -2.0f || fx0 > (float)(c->W + 1) || fy0 > (float)(c->H + 1)) return;
     x0 = (int)fmaxf(floorf(fx0) - 1.0f, 0.0f);
     y0 = (int)fmaxf(floorf(fy0) - 1.0f, 0.0f);
     x1 = (int)fminf(ceilf(fx1) + 1.0f, (float)(c->W - 1));
     y1 = (int)fminf(ceilf(fy1) + 1.0f, (float)(c->H - 1));
-  } else if (fmaxf(zA, fmaxf(zB, zC)) < c->znear) {
-    return; /* entirely in front of the near plane */
   }
   int own0 = edge_owns_zero(n0), own1 = edge_owns_zero(n1), own2 = edge_owns_zero(n2);
   for (int py = y0; py <= y1; ++py) {
