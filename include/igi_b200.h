@@ -119,6 +119,7 @@ typedef struct IgiSensorParams {
   float grid_org[3], grid_h, grid_slack; /* conservative gel-interior distance grid */
   int32_t grid_n[3];
   float depth0_max;
+  int32_t hiz_levels, hiz_off[10], hiz_w[10]; /* depth0 max-pyramid layout (IgiTactileStatic.hiz) */
   float area_w_full, area_w_half; /* cv2 INTER_AREA 3.5x taps as float32: 2/7 and 1/7 */
 } IgiSensorParams;
 
@@ -139,6 +140,7 @@ typedef struct IgiTactileStatic {
   const uint8_t* bg_real;       /* (n_bg,H,W,3) real reference frames, renderer.py:555-558 */
   const float* obs_empty;       /* (2048)  observation of a no-contact frame */
   const float* grid;            /* (nz,ny,nx) distance grid */
+  const float* hiz;             /* max-pyramid of depth0, level l at hiz + hiz_off[l], row length hiz_w[l] */
 } IgiTactileStatic;
 
 /* Per-step inputs (device): poses exactly as update_tactile gathers them

@@ -43,6 +43,7 @@ class IgiSensorParams(_c.Structure):
         ("blur_ksize", _c.c_int32), ("gauss", _c.c_float * 7),
         ("grid_org", _c.c_float * 3), ("grid_h", _c.c_float), ("grid_slack", _c.c_float),
         ("grid_n", _c.c_int32 * 3), ("depth0_max", _c.c_float),
+        ("hiz_levels", _c.c_int32), ("hiz_off", _c.c_int32 * 10), ("hiz_w", _c.c_int32 * 10),
         ("area_w_full", _c.c_float), ("area_w_half", _c.c_float),
     ]
 
@@ -54,7 +55,7 @@ class IgiTactileMeshes(_c.Structure):
 
 class IgiTactileStatic(_c.Structure):
     _fields_ = [("depth0", _c.c_void_p), ("bg_sim", _c.c_void_p), ("bg_real", _c.c_void_p),
-                ("obs_empty", _c.c_void_p), ("grid", _c.c_void_p)]
+                ("obs_empty", _c.c_void_p), ("grid", _c.c_void_p), ("hiz", _c.c_void_p)]
 
 
 class IgiTactileFrames(_c.Structure):
@@ -193,15 +194,33 @@ class MeshTable:
         self.max_clusters = int(self.info[:, 3].max())
 
 
-def gel_interior_grid(depth0, dxp, dyp, h=0.0005):
+def depth_max_pyramid(depth0):
+    """Max-pyramid of depth0 for hierarchical-Z culling: (flat f32, offsets, widths)."""
+    cur = np.where(depth0 > 0, depth0, np.inf).astype(np.float32)
+    levels, offs, widths, off = [], [], [], 0
+    while True:
+        levels.append(cur.ravel())
+        offs.append(off)
+        widths.append(cur.shape[1])
+        off += cur.size
+        if cur.shape[0] == 1 and cur.shape[1] == 1:
+            break
+        hh, ww = (cur.shape[0] + 1) // 2, (cur.shape[1] + 1) // 2
+        pad = np.full((hh * 2, ww * 2), -np.inf, dtype=np.float32)
+        pad[:cur.shape[0], :cur.shape[1]] = cur
+        cur = pad.reshape(hh, 2, ww, 2).max(axis=(1, 3))
+    return np.concatenate(levels).astype(np.float32), offs, widths
+
+
+def gel_interior_grid(depth0, dxp, dyp, h=0.00025):
     """Conservative distance grid to the visible gel interior {points nearer than depth0
     along their pixel ray}, camera frame (x right, y up, depth forward).  Returns
     (grid f32 (nz,ny,nx) metres, origin (3,), h, slack)."""
-    d0 = depth0.astype(np.float64)
+    d0 = depth0.astype(np.float32)
     d0 = np.where(d0 > 0, d0, d0.max())
-    ss = np.linspace(0.0, 1.0, 72)
-    X = (dxp[None, :, None] * d0[:, :, None] * ss)
-    Y = (dyp[:, None, None] * d0[:, :, None] * ss)
+    ss = np.linspace(0.0, 1.0, 128, dtype=np.float32)   # <= 0.2 mm between samples along a ray
+    X = (dxp[None, :, None].astype(np.float32) * d0[:, :, None] * ss)
+    Y = (dyp[:, None, None].astype(np.float32) * d0[:, :, None] * ss)
     Z = d0[:, :, None] * ss
     lo = np.array([X.min(), Y.min(), 0.0]) - 2 * h
     hi = np.array([X.max(), Y.max(), Z.max()]) + 2 * h
@@ -257,6 +276,7 @@ class BatchedAllSight:
         self.depth0 = torch.empty((H, W), dtype=torch.float32, device=dev)
         self.bg_sim = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
         self._grid = torch.zeros((1, 1, 1), dtype=torch.float32, device=dev)
+        self._hiz_layout = ([0], [1])
         self._upload_sensor(np.zeros(3, np.float32), 1.0, 1.0, (1, 1, 1), 1.0)
         zbuf = torch.empty((H * W,), dtype=torch.int64, device=dev)
         rc = self.lib.igi_tactile_gel_precompute(_lib.dptr(self._gel), _c.c_int(self._gel.shape[0]), _lib.dptr(zbuf),
@@ -266,6 +286,9 @@ class BatchedAllSight:
         d0 = self.depth0.cpu().numpy()
         grid, org, h, slack = gel_interior_grid(d0, self.cfg.dxp, self.cfg.dyp)
         self._grid = torch.from_numpy(grid).to(dev).contiguous()
+        hiz, offs, widths = depth_max_pyramid(d0)
+        self._hiz = torch.from_numpy(hiz).to(dev)
+        self._hiz_layout = (offs, widths)
         self._upload_sensor(org, h, slack, grid.shape[::-1], float(d0.max()))
         self.mask = circle_mask((W, H))
 
@@ -312,6 +335,10 @@ class BatchedAllSight:
         p.grid_h, p.grid_slack = h, slack
         p.grid_n = (_c.c_int32 * 3)(*[int(v) for v in n_xyz])
         p.depth0_max = d0max
+        offs, widths = self._hiz_layout
+        p.hiz_levels = len(offs)
+        p.hiz_off = (_c.c_int32 * 10)(*(list(offs) + [0] * (10 - len(offs))))
+        p.hiz_w = (_c.c_int32 * 10)(*(list(widths) + [1] * (10 - len(widths))))
         p.area_w_full = float(np.float32(1.0 / 3.5))
         p.area_w_half = float(np.float32(0.5 / 3.5))
         with torch.cuda.device(self.device):
@@ -323,7 +350,7 @@ class BatchedAllSight:
         m.face_orig, m.meshes, m.clusters = self._face_orig.data_ptr(), self._minfo.data_ptr(), self._clusters.data_ptr()
         st = IgiTactileStatic()
         st.depth0, st.bg_sim, st.bg_real = self.depth0.data_ptr(), self.bg_sim.data_ptr(), self.bg_real.data_ptr()
-        st.obs_empty, st.grid = self.obs_empty.data_ptr(), self._grid.data_ptr()
+        st.obs_empty, st.grid, st.hiz = self.obs_empty.data_ptr(), self._grid.data_ptr(), self._hiz.data_ptr()
         sc = IgiTactileScratch()
         sc.M, sc.setups, sc.counts = self._M.data_ptr(), self._setups.data_ptr(), self._counts.data_ptr()
         sc.bbox, sc.worklist, sc.counters, sc.kmax = (self._bbox.data_ptr(), self._work.data_ptr(),

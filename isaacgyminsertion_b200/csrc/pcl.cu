@@ -238,11 +238,13 @@ struct FpsCand {
 __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_t task_stride,
                                                         const int32_t* count, const int32_t* any,
                                                         int64_t count_stride, int n_fixed, int m,
-                                                        float* out_pts, int64_t out_stride, int32_t* out_idx) {
+                                                        float* out_pts, int64_t out_stride, int32_t* out_idx,
+                                                        int min_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int task = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = count ? count[(size_t)task * count_stride] : n_fixed;
+  if (n < min_n) return;  // small tasks belong to fps_warp_kernel
   const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
   float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
   int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
@@ -314,6 +316,94 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
   }
 }
 
+// Warp-per-task FPS for the common small clouds (n <= FW_MAXN): the task's points sit in a
+// per-warp SoA slice of shared memory, running minimum distances and tie keys in registers,
+// the arg-max is two REDUX instructions, no block barrier anywhere.  Same selection rule as
+// fps_kernel (and oracle/fps.py).
+constexpr int FW_WARPS = 8, FW_MAXN = 384, FW_PPL = FW_MAXN / 32;
+
+__global__ void __launch_bounds__(FW_WARPS * 32) fps_warp_kernel(const float* pts, int64_t task_stride,
+                                                                 const int32_t* count, const int32_t* any,
+                                                                 int64_t count_stride, int n_fixed, int n_tasks,
+                                                                 int m, float* out_pts, int64_t out_stride,
+                                                                 int32_t* out_idx) {
+  __shared__ float s_p[FW_WARPS][3][FW_MAXN];
+  extern __shared__ unsigned short s_sel_all[];  // FW_WARPS * m selected indices (n <= 384 fits 16 bits)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int task = blockIdx.x * FW_WARPS + warp;
+  if (task >= n_tasks) return;
+  const int n = count ? count[(size_t)task * count_stride] : n_fixed;
+  const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
+  float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
+  int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
+  if (!live) {
+    for (int i = lane; i < m; i += 32) {
+      if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
+      if (idst) idst[i] = 0;
+    }
+    return;
+  }
+  if (n > FW_MAXN) return;  // fps_kernel handles it
+  float* sx = s_p[warp][0];
+  float* sy = s_p[warp][1];
+  float* sz = s_p[warp][2];
+  unsigned short* sel = s_sel_all + warp * m;
+  const float* src = pts + (size_t)task * task_stride;
+  for (int i = lane; i < 3 * n; i += 32) {
+    const float v = src[i];
+    const int k = i / 3, c = i - 3 * k;
+    s_p[warp][c][k] = v;
+  }
+  __syncwarp();
+  int lg = 31 - __clz(n);
+  if (lg > 9) lg = 9;
+  const uint32_t bmask = (1u << lg) - 1u;
+  float temp[FW_PPL];
+  uint32_t lokey[FW_PPL];  // 0 = not a candidate
+#pragma unroll
+  for (int i = 0; i < FW_PPL; ++i) {
+    const int k = lane + 32 * i;
+    temp[i] = 1e10f;
+    lokey[i] = 0u;
+    if (k < n) {
+      const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
+      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+      if (mag > 1e-3f) {
+        const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
+        lokey[i] = ~((rev << 16) | (uint32_t)k);
+      }
+    }
+  }
+  int old = 0;
+  if (lane == 0) sel[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    uint32_t bhi = 0, blo = 0;
+#pragma unroll
+    for (int i = 0; i < FW_PPL; ++i) {
+      const int k = lane + 32 * i;
+      if (lokey[i] != 0u) {
+        const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d2 = fminf(d, temp[i]);
+        temp[i] = d2;
+        const uint32_t hi = __float_as_uint(d2) + 1u;
+        if (hi > bhi || (hi == bhi && lokey[i] > blo)) { bhi = hi; blo = lokey[i]; }
+      }
+    }
+    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
+    old = (whi == 0) ? 0 : (int)((~wlo) & 0xffffu);
+    if (lane == 0) sel[j] = (unsigned short)old;
+  }
+  __syncwarp();
+  for (int i = lane; i < m; i += 32) {
+    const int k = sel[i];
+    if (idst) idst[i] = k;
+    if (dst) { dst[i * 3 + 0] = sx[k]; dst[i * 3 + 1] = sy[k]; dst[i * 3 + 2] = sz[k]; }
+  }
+}
+
 }  // namespace
 
 extern "C" int igi_pcl_compact(const float* depth, const int32_t* seg, const int32_t* seg_ids, int n_classes,
@@ -376,18 +466,29 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
   IGI_REQUIRE(count || n_fixed > 0, "igi_fps: need count or n_fixed");
   IGI_REQUIRE(!out_pts || out_stride >= (int64_t)m * 3, "igi_fps: out_stride < 3*m");
   if (n_tasks == 0) return IGI_OK;
-  // worst-case dynamic smem: task_stride/3 points (count is on the device)
+  cudaStream_t st = (cudaStream_t)stream;
   const int64_t nmax = count ? task_stride / 3 : n_fixed;
   IGI_REQUIRE(nmax <= 0xffff, "igi_fps: at most 65535 points per task");
-  const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
-  IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  const bool warp_ok = (size_t)FW_WARPS * m * 2 <= 48 * 1024 - sizeof(float) * FW_WARPS * 3 * FW_MAXN;
+  const bool need_block = !warp_ok || nmax > FW_MAXN;
+  const bool need_warp = warp_ok && (count != nullptr || n_fixed <= FW_MAXN);
+  if (need_warp) {
+    fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, (size_t)FW_WARPS * m * 2, st>>>(
+        pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m, out_pts, out_stride, out_idx);
+    IGI_CHECK_LAUNCH("fps_warp_kernel");
   }
-  fps_kernel<<<n_tasks, kFpsBlock, smem, (cudaStream_t)stream>>>(pts, task_stride, count, any, count_stride,
-                                                                 n_fixed, m, out_pts, out_stride, out_idx);
-  IGI_CHECK_LAUNCH("fps_kernel");
+  if (need_block) {
+    // worst-case dynamic smem: task_stride/3 points (count is on the device)
+    const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
+    IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
+    fps_kernel<<<n_tasks, kFpsBlock, smem, st>>>(pts, task_stride, count, any, count_stride, n_fixed, m, out_pts,
+                                                 out_stride, out_idx, need_warp ? FW_MAXN + 1 : 0);
+    IGI_CHECK_LAUNCH("fps_kernel");
+  }
   return IGI_OK;
 }

@@ -39,6 +39,7 @@ struct TacConst {
   float grid_org[3], grid_h, grid_slack;
   int grid_n[3];
   float depth0_max;
+  int hiz_levels, hiz_off[10], hiz_w[10];  // max-pyramid of depth0 (level 0 = full resolution)
   float area_w[5];  // INTER_AREA 3.5x taps (f32 as cv2 stores them): even dst: w0 w0 w0 w1, odd: w1 w0 w0 w0
 };
 __constant__ TacConst kc;
@@ -254,6 +255,7 @@ struct GeomArgs {
   const int32_t* faces;      // (nf,3) global vertex ids, cluster order
   const int32_t* face_orig;  // (nf)
   const float* grid;         // distance grid
+  const float* hiz;          // depth0 max-pyramid
   float* M_out;              // (F,12)
   Setup* setups;             // (F, kmax)
   int32_t* counts;           // (F)   surviving triangles (may exceed kmax -> overflow)
@@ -373,6 +375,16 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
       if (grid_lower_bound(a.grid, gx, gy, gz) > rr) continue;
       int x0, y0, x1, y1;
       if (!tri_bbox(A, B, C, x0, y0, x1, y1)) continue;
+      {  // hierarchical-Z: nearest possible fragment vs the farthest gel depth under the box
+        int L = 0;
+        while (L < kc.hiz_levels - 1 && (((x1 >> L) - (x0 >> L)) > 1 || ((y1 >> L) - (y0 >> L)) > 1)) ++L;
+        const float* hz = a.hiz + kc.hiz_off[L];
+        const int hw = kc.hiz_w[L];
+        const int ax = x0 >> L, bx = x1 >> L, ay = y0 >> L, by = y1 >> L;
+        const float m = fmaxf(fmaxf(hz[ay * hw + ax], hz[ay * hw + bx]), fmaxf(hz[by * hw + ax], hz[by * hw + bx]));
+        const float zmin = fmaxf(fminf(-A.z, fminf(-B.z, -C.z)), kc.znear);
+        if (zmin > m) continue;
+      }
       s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
       s.tri = (uint32_t)face;
       s.orig = (uint32_t)a.face_orig[face];
@@ -466,18 +478,47 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
+constexpr int CT_LARGE_AREA = 48;   // bbox area (px) above which a triangle is rastered by a whole warp
+constexpr int CT_LARGE_MAX = 1024;
+
+__device__ __forceinline__ Setup load_setup(const Setup* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  union { uint4 v[4]; Setup s; } u;
+  u.v[0] = __ldg(q); u.v[1] = __ldg(q + 1); u.v[2] = __ldg(q + 2); u.v[3] = __ldg(q + 3);
+  return u.s;
+}
+
+__device__ __forceinline__ void raster_px(const Setup& s, int k, int px, int py, int rx0, int ry0,
+                                          const float* __restrict__ depth0, unsigned long long* s_z, int* s_hits) {
+  float e1, e2, es;
+  const float t = cover(s, px, py, e1, e2, es);
+  if (t < 0.0f) return;
+  const float d0 = __ldg(depth0 + py * TW + px);
+  if (d0 != 0.0f && !(t < d0)) return;  // GL_LESS against the gel
+  const unsigned long long key =
+      ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)s.orig << 12) | (uint32_t)k;
+  unsigned long long* zp = &s_z[(py - ry0) * REG + (px - rx0)];
+  if (key < *zp) {
+    atomicMin(zp, key);
+    *s_hits = 1;
+  }
+}
+
 __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
   __shared__ unsigned long long s_z[REG * REG];   // depth<<32 | orig<<12 | slot
   __shared__ float s_diff[REG * REG * 3];         // (c - bg_sim) * scale
   __shared__ float s_h[REG * TILE * 3];           // horizontal blur
   __shared__ float sM[12];
-  __shared__ int s_frame;
-  const int tid = threadIdx.x;
+  __shared__ int s_large[CT_LARGE_MAX];
+  __shared__ int s_nlarge, s_hits, s_frame;
+  __shared__ int s_hb[4];                         // bounds of the tiles that produced hits
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
       const int w = atomicAdd(a.cursor, 1);
       s_frame = (w < *a.work_n) ? a.worklist[w] : -1;
+      s_hb[0] = TW; s_hb[1] = TH; s_hb[2] = -1; s_hb[3] = -1;
     }
     __syncthreads();
     const int f = s_frame;
@@ -485,40 +526,54 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
     if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const int K = a.counts[f];
     const Setup* list = a.setups + (size_t)f * a.kmax;
-    // dirty window: triangle bbox dilated by the blur radius
+    // candidate window: union of the triangle boxes, dilated by the blur radius
     const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
     const int wx1 = min(a.bbox[4 * f + 2] + HALO, TW - 1), wy1 = min(a.bbox[4 * f + 3] + HALO, TH - 1);
     const uint8_t* bgr = a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3;
     uint8_t* col = a.color + (size_t)f * TW * TH * 3;
     float* gdep = a.gel_depth + (size_t)f * TW * TH;
-    __syncthreads();
 
     for (int ty = wy0; ty <= wy1; ty += TILE)
       for (int tx = wx0; tx <= wx1; tx += TILE) {
-        // region = tile + halo, in image coordinates [rx0, rx0+REG) x [ry0, ry0+REG)
+        // region = tile + halo, image coordinates [rx0, rx0+REG) x [ry0, ry0+REG)
         const int rx0 = tx - HALO, ry0 = ty - HALO;
-        for (int i = tid; i < REG * REG; i += CT_BLOCK) s_z[i] = ZEMPTY;
+        const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
+        const int cx1 = min(rx0 + REG - 1, TW - 1), cy1 = min(ry0 + REG - 1, TH - 1);
         __syncthreads();
-        // --- raster: one thread per triangle, pixels of bbox ∩ region
+        for (int i = tid; i < REG * REG; i += CT_BLOCK) s_z[i] = ZEMPTY;
+        if (tid == 0) { s_nlarge = 0; s_hits = 0; }
+        __syncthreads();
+        // --- pass A: one thread per small triangle; large ones are queued for pass B
         for (int k = tid; k < K; k += CT_BLOCK) {
-          const Setup s = list[k];
-          const int bx0 = max((int)(s.bbox & 255u), max(rx0, 0)), by0 = max((int)((s.bbox >> 8) & 255u), max(ry0, 0));
-          const int bx1 = min((int)((s.bbox >> 16) & 255u), min(rx0 + REG - 1, TW - 1));
-          const int by1 = min((int)(s.bbox >> 24), min(ry0 + REG - 1, TH - 1));
+          const uint32_t bb = __ldg(&list[k].bbox);
+          const int bx0 = max((int)(bb & 255u), cx0), by0 = max((int)((bb >> 8) & 255u), cy0);
+          const int bx1 = min((int)((bb >> 16) & 255u), cx1), by1 = min((int)(bb >> 24), cy1);
+          if (bx0 > bx1 || by0 > by1) continue;
+          if ((bx1 - bx0 + 1) * (by1 - by0 + 1) > CT_LARGE_AREA) {
+            const int slot = atomicAdd(&s_nlarge, 1);
+            if (slot < CT_LARGE_MAX) { s_large[slot] = k; continue; }
+          }
+          const Setup s = load_setup(list + k);
           for (int py = by0; py <= by1; ++py)
-            for (int px = bx0; px <= bx1; ++px) {
-              float e1, e2, es;
-              const float t = cover(s, px, py, e1, e2, es);
-              if (t < 0.0f) continue;
-              const float d0 = a.depth0[py * TW + px];
-              if (d0 != 0.0f && !(t < d0)) continue;  // GL_LESS against the gel
-              const unsigned long long key =
-                  ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)s.orig << 12) | (uint32_t)k;
-              unsigned long long* zp = &s_z[(py - ry0) * REG + (px - rx0)];
-              if (key < *zp) atomicMin(zp, key);
-            }
+            for (int px = bx0; px <= bx1; ++px) raster_px(s, k, px, py, rx0, ry0, a.depth0, s_z, &s_hits);
         }
         __syncthreads();
+        // --- pass B: one warp per large triangle, lanes stride over its clipped box
+        const int nl = min(s_nlarge, CT_LARGE_MAX);
+        for (int idx = warp; idx < nl; idx += CT_BLOCK / 32) {
+          const int k = s_large[idx];
+          const Setup s = load_setup(list + k);
+          const int bx0 = max((int)(s.bbox & 255u), cx0), by0 = max((int)((s.bbox >> 8) & 255u), cy0);
+          const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1), by1 = min((int)(s.bbox >> 24), cy1);
+          const int bw = bx1 - bx0 + 1, np = bw * (by1 - by0 + 1);
+          for (int i = lane; i < np; i += 32) raster_px(s, k, bx0 + i % bw, by0 + i / bw, rx0, ry0, a.depth0, s_z, &s_hits);
+        }
+        __syncthreads();
+        if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
+        if (tid == 0) {
+          s_hb[0] = min(s_hb[0], cx0); s_hb[1] = min(s_hb[1], cy0);
+          s_hb[2] = max(s_hb[2], cx1); s_hb[3] = max(s_hb[3], cy1);
+        }
         // --- shade hits, build the scaled difference image (0 where the gel is visible)
         for (int i = tid; i < REG * REG; i += CT_BLOCK) {
           const unsigned long long key = s_z[i];
@@ -526,7 +581,7 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
           const int px = rx0 + i % REG, py = ry0 + i / REG;
           if (key != ZEMPTY) {
             const float t = __uint_as_float((uint32_t)(key >> 32));
-            const Setup s = list[(int)(key & 0xfffu)];
+            const Setup s = load_setup(list + (int)(key & 0xfffu));
             const float dx = k_dxp[px], dy = k_dyp[py];
             const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
             const float es = add(add(e0, e1), e2);
@@ -593,14 +648,15 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
             col[o + c] = (uint8_t)v;
           }
         }
-        __syncthreads();
       }
-    // --- obs pixels whose 3.5x3.5 source window meets the dirty window -----------------------
+    __syncthreads();
+    // --- obs pixels whose 3.5x3.5 source window meets a tile that changed -----------------------
     // flipud + crop: obs row r reads flipped rows [3.5r, 3.5r+3.5) = original rows 223 - that.
-    {
-      const int fy_lo = TH - 1 - wy1, fy_hi = TH - 1 - wy0;  // dirty rows in flipped coordinates
+    if (s_hb[2] >= 0) {
+      const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
+      const int fy_lo = TH - 1 - hy1, fy_hi = TH - 1 - hy0;  // changed rows in flipped coordinates
       const int oy0 = max((2 * fy_lo) / 7 - 1, 0), oy1 = min((2 * fy_hi) / 7 + 1, OBS_H - 1);
-      const int ox0 = max((2 * wx0) / 7 - 1, 0), ox1 = min((2 * wx1) / 7 + 1, OBS_W - 1);
+      const int ox0 = max((2 * hx0) / 7 - 1, 0), ox1 = min((2 * hx1) / 7 + 1, OBS_W - 1);
       const int nw = ox1 - ox0 + 1, nh = oy1 - oy0 + 1;
       float* ob = a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
                   (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride;
@@ -710,6 +766,9 @@ extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
   c.grid_h = p->grid_h;
   c.grid_slack = p->grid_slack;
   c.depth0_max = p->depth0_max;
+  IGI_REQUIRE(p->hiz_levels >= 1 && p->hiz_levels <= 10, "igi_tactile_set_sensor: hiz_levels must be 1..10");
+  c.hiz_levels = p->hiz_levels;
+  for (int k = 0; k < p->hiz_levels; ++k) { c.hiz_off[k] = p->hiz_off[k]; c.hiz_w[k] = p->hiz_w[k]; }
   c.area_w[0] = p->area_w_full;
   c.area_w[1] = p->area_w_half;
   IGI_CUDA(cudaMemcpyToSymbol(kc, &c, sizeof(c)));
@@ -738,7 +797,8 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
               "igi_tactile_render: null pose pointer");
   IGI_REQUIRE(m->verts && m->vnorm && m->faces && m->face_orig && m->meshes && m->clusters,
               "igi_tactile_render: null mesh pointer");
-  IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid, "igi_tactile_render: null static pointer");
+  IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid && st->hiz,
+              "igi_tactile_render: null static pointer");
   IGI_REQUIRE(sc->M && sc->setups && sc->counts && sc->bbox && sc->worklist && sc->counters && sc->kmax > 0 &&
                   sc->kmax <= 4096,
               "igi_tactile_render: bad scratch (kmax must be 1..4096)");
@@ -758,7 +818,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
   g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
-  g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid;
+  g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz;
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
