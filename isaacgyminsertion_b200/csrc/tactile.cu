@@ -30,6 +30,9 @@ struct TacConst {
   float light_int[MAX_LIGHTS], light_las[MAX_LIGHTS], light_lao[MAX_LIGHTS];
   int inverse_square;
   float base[3], metallic, roughness;
+  // shading constants derived from the material / lights at upload time
+  float sh_a2, sh_f90, sh_f0[3], sh_cdiff_pi[3], sh_rad[MAX_LIGHTS][3];
+  int gray;  // 1: material and lights are colourless -> the three channels are identical
   double cam_R[9], cam_p[3];  // camera zero pose in the sensor frame
   float gel_camx;
   double max_force, max_deformation;
@@ -141,6 +144,28 @@ __device__ __forceinline__ float cover(const Setup& s, int px, int py, float& e1
   return t;
 }
 
+
+// Conservative test of one image-aligned 8x8 block (clipped to [x0,x1]x[y0,y1]) against a
+// triangle: false when the block lies outside an edge plane, or when the nearest depth of the
+// triangle's plane over the block is behind the farthest gel depth of the block (hzmax).  Edge
+// functions and the depth denominator are affine in the ray slopes, so their extreme over the
+// block sits at a corner; a relative margin keeps the bound conservative against the
+// separately-rounded per-pixel arithmetic of cover().
+__device__ __forceinline__ bool block_may_hit(const Setup& s, int x0, int x1, int y0, int y1, float hzmax) {
+  const float dxa = k_dxp[x0], dxb = k_dxp[x1], dya = k_dyp[y0], dyb = k_dyp[y1];
+  auto lo_bound = [&](V3 n) {  // lower bound of dx*n.x + dy*n.y - n.z over the block
+    const float ax = fminf(dxa * n.x, dxb * n.x), ay = fminf(dya * n.y, dyb * n.y);
+    const float m = 1e-5f * (fmaxf(fabsf(dxa * n.x), fabsf(dxb * n.x)) +
+                             fmaxf(fabsf(dya * n.y), fabsf(dyb * n.y)) + fabsf(n.z));
+    return ax + ay - n.z - m;
+  };
+  if (lo_bound(s.n0) > 0.0f || lo_bound(s.n1) > 0.0f || lo_bound(s.n2) > 0.0f) return false;
+  const float den_lo = lo_bound(s.N);  // most negative denominator -> nearest depth
+  if (!(den_lo < 0.0f)) return false;  // plane never faces these rays
+  const float tmin = (s.det / den_lo) * (1.0f - 1e-5f);
+  return tmin < hzmax;
+}
+
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ V3 normalize(V3 v) {
   float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
@@ -148,51 +173,58 @@ __device__ __forceinline__ V3 normalize(V3 v) {
   return v;
 }
 
-// pyrender mesh.frag (metallic-roughness, spot lights) -> 8-bit UNORM rgb
-__device__ void shade(V3 p, V3 n, uint8_t* rgb) {
-  const float PI = 3.14159265358979323846f;
-  V3 v = normalize(V3{-p.x, -p.y, -p.z});
-  float f0[3], cdiff[3], col[3] = {0.f, 0.f, 0.f};
+// pyrender mesh.frag (metallic-roughness, spot lights) -> 8-bit UNORM rgb.
+// NCH = 1 when material and lights are colourless (r == g == b), else 3.  Uses the fast
+// reciprocal / rsqrt / exp2-log2 paths: the result feeds an 8-bit quantiser and is compared with
+// the oracle within 1/255.
+template <int NCH>
+__device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
+  const float INV_PI = 0.31830988618379067f;
+  const float ipl = rsqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+  const V3 v{-p.x * ipl, -p.y * ipl, -p.z * ipl};
+  const float a2 = kc.sh_a2;
+  const float nv = clampf(n.x * v.x + n.y * v.y + n.z * v.z, 0.001f, 1.0f);
+  const float av = __fdividef(2.0f * nv, nv + sqrtf(a2 + (1.0f - a2) * (nv * nv)));
+  float col[NCH];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    f0[k] = 0.04f * (1.0f - kc.metallic) + kc.base[k] * kc.metallic;
-    cdiff[k] = kc.base[k] * (1.0f - 0.04f) * (1.0f - kc.metallic);
-  }
-  const float f90 = clampf(fmaxf(fmaxf(f0[0], f0[1]), f0[2]) * 25.0f, 0.0f, 1.0f);
-  const float alpha = kc.roughness * kc.roughness, a2 = alpha * alpha;
+  for (int k = 0; k < NCH; ++k) col[k] = 0.f;
   for (int i = 0; i < kc.n_lights; ++i) {
-    V3 L{kc.light_pos[i][0] - p.x, kc.light_pos[i][1] - p.y, kc.light_pos[i][2] - p.z};
+    const V3 L{kc.light_pos[i][0] - p.x, kc.light_pos[i][1] - p.y, kc.light_pos[i][2] - p.z};
     const float d2 = L.x * L.x + L.y * L.y + L.z * L.z;
-    V3 l = normalize(L);
-    V3 h = normalize(V3{l.x + v.x, l.y + v.y, l.z + v.z});
+    const float il = rsqrtf(d2);
+    const V3 l{L.x * il, L.y * il, L.z * il};
+    V3 h{l.x + v.x, l.y + v.y, l.z + v.z};
+    const float ih = rsqrtf(h.x * h.x + h.y * h.y + h.z * h.z);
+    h.x *= ih; h.y *= ih; h.z *= ih;
     const float nl = clampf(n.x * l.x + n.y * l.y + n.z * l.z, 0.001f, 1.0f);
-    const float nv = clampf(n.x * v.x + n.y * v.y + n.z * v.z, 0.001f, 1.0f);
     const float nh = clampf(n.x * h.x + n.y * h.y + n.z * h.z, 0.001f, 1.0f);
     const float vh = clampf(v.x * h.x + v.y * h.y + v.z * h.z, 0.001f, 1.0f);
     const float cd = -(kc.light_dir[i][0] * l.x + kc.light_dir[i][1] * l.y + kc.light_dir[i][2] * l.z);
     float att = clampf(cd * kc.light_las[i] + kc.light_lao[i], 0.0f, 1.0f);
     att = att * att;
-    if (kc.inverse_square) att = att / d2;
-    const float w = clampf(1.0f - vh, 0.0f, 1.0f);
+    if (kc.inverse_square) att = att * il * il;
+    const float w = 1.0f - vh;
     const float w2 = w * w, fw = w2 * w2 * w;
-    const float al = 2.0f * nl / (nl + sqrtf(a2 + (1.0f - a2) * (nl * nl)));
-    const float av = 2.0f * nv / (nv + sqrtf(a2 + (1.0f - a2) * (nv * nv)));
-    const float G = al * av;
+    const float al = __fdividef(2.0f * nl, nl + sqrtf(a2 + (1.0f - a2) * (nl * nl)));
     const float f = (nh * a2 - nh) * nh + 1.0f;
-    const float D = a2 / (PI * f * f);
+    const float D = __fdividef(a2 * INV_PI, f * f);
+    const float sp = __fdividef(al * av * D, 4.0f * nl * nv);
+    const float na = nl * att;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float F = f0[k] + (f90 - f0[k]) * fw;
-      const float diffuse = (1.0f - F) * cdiff[k] / PI;
-      const float spec = F * G * D / (4.0f * nl * nv);
-      col[k] += nl * (att * kc.light_col[i][k] * kc.light_int[i]) * (diffuse + spec);
+    for (int k = 0; k < NCH; ++k) {
+      const float F = kc.sh_f0[k] + (kc.sh_f90 - kc.sh_f0[k]) * fw;
+      col[k] += na * kc.sh_rad[i][k] * ((1.0f - F) * kc.sh_cdiff_pi[k] + F * sp);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float o = clampf(powf(col[k], 1.0f / 2.2f), 0.0f, 1.0f);
+  for (int k = 0; k < NCH; ++k) {
+    const float o = clampf(__powf(col[k], 1.0f / 2.2f), 0.0f, 1.0f);
     rgb[k] = (uint8_t)floorf(o * 255.0f + 0.5f);
   }
+  if (NCH == 1) rgb[1] = rgb[2] = rgb[0];
+}
+__device__ __forceinline__ void shade(V3 p, V3 n, uint8_t* rgb) {
+  if (kc.gray) shade_t<1>(p, n, rgb); else shade_t<3>(p, n, rgb);
 }
 
 // ---- K0: static gel -------------------------------------------------------------------
@@ -256,6 +288,7 @@ struct GeomArgs {
   const int32_t* face_orig;  // (nf)
   const float* grid;         // distance grid
   const float* hiz;          // depth0 max-pyramid
+  const float* depth0;       // (TH,TW)
   float* M_out;              // (F,12)
   Setup* setups;             // (F, kmax)
   int32_t* counts;           // (F)   surviving triangles (may exceed kmax -> overflow)
@@ -285,6 +318,7 @@ __device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid
 
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
+constexpr int GEOM_EXACT_AREA = 100;  // boxes up to this many pixels are visibility-tested exactly
 
 __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
   __shared__ float sM[12];
@@ -385,6 +419,34 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
         const float zmin = fmaxf(fminf(-A.z, fminf(-B.z, -C.z)), kc.znear);
         if (zmin > m) continue;
       }
+      // visibility against the gel: small boxes are scanned exactly (same arithmetic as the
+      // raster), large ones block by block with the conservative bound; invisible triangles are
+      // dropped here so the contact kernel only sees what can produce a fragment
+      if ((x1 - x0 + 1) * (y1 - y0 + 1) <= GEOM_EXACT_AREA) {
+        bool vis = false;
+        for (int py = y0; py <= y1 && !vis; ++py)
+          for (int px = x0; px <= x1; ++px) {
+            float e1, e2, es;
+            const float t = cover(s, px, py, e1, e2, es);
+            if (t < 0.0f) continue;
+            const float d0 = __ldg(a.depth0 + py * TW + px);
+            if (d0 == 0.0f || t < d0) { vis = true; break; }
+          }
+        if (!vis) continue;
+      } else {
+        const float* hz3 = a.hiz + kc.hiz_off[3];
+        const int hw3 = kc.hiz_w[3];
+        int vx0 = TW, vy0 = TH, vx1 = -1, vy1 = -1;
+        for (int gy = y0 >> 3; gy <= (y1 >> 3); ++gy)
+          for (int gx = x0 >> 3; gx <= (x1 >> 3); ++gx) {
+            const int cx0 = max(gx * 8, x0), cx1 = min(gx * 8 + 7, x1), cy0 = max(gy * 8, y0), cy1 = min(gy * 8 + 7, y1);
+            if (block_may_hit(s, cx0, cx1, cy0, cy1, hz3[gy * hw3 + gx])) {
+              vx0 = min(vx0, cx0); vy0 = min(vy0, cy0); vx1 = max(vx1, cx1); vy1 = max(vy1, cy1);
+            }
+          }
+        if (vx1 < 0) continue;
+        x0 = vx0; y0 = vy0; x1 = vx1; y1 = vy1;  // shrink the box to the blocks that may hit
+      }
       s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
       s.tri = (uint32_t)face;
       s.orig = (uint32_t)a.face_orig[face];
@@ -460,6 +522,7 @@ struct ContactArgs {
   const float* vnorm;
   const int32_t* faces;
   const float* depth0;       // (TH,TW)
+  const float* hiz;          // depth0 max-pyramid
   const uint8_t* bg_sim;     // (TH,TW,3)
   const uint8_t* bg_real;
   const int32_t* bg_id;
@@ -504,10 +567,11 @@ __device__ __forceinline__ void raster_px(const Setup& s, int k, int px, int py,
   }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
   __shared__ unsigned long long s_z[REG * REG];   // depth<<32 | orig<<12 | slot
-  __shared__ float s_diff[REG * REG * 3];         // (c - bg_sim) * scale
-  __shared__ float s_h[REG * TILE * 3];           // horizontal blur
+  __shared__ float s_diff[REG * REG * NCH];       // (c - bg_sim) * scale
+  __shared__ float s_h[REG * TILE * NCH];         // horizontal blur
   __shared__ float sM[12];
   __shared__ int s_large[CT_LARGE_MAX];
   __shared__ int s_nlarge, s_hits, s_frame;
@@ -558,15 +622,45 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
             for (int px = bx0; px <= bx1; ++px) raster_px(s, k, px, py, rx0, ry0, a.depth0, s_z, &s_hits);
         }
         __syncthreads();
-        // --- pass B: one warp per large triangle, lanes stride over its clipped box
+        // --- pass B: one warp per large triangle.  Its clipped box is cut into image-aligned 8x8
+        // blocks; a block is dropped when it lies outside an edge plane or when the nearest depth
+        // of the triangle's plane over the block is behind the farthest gel depth of the block
+        // (level 3 of the depth0 max-pyramid).  Both bounds are affine in the ray slopes, so the
+        // extreme over a block sits at a corner; a relative margin keeps them conservative against
+        // the separately-rounded per-pixel arithmetic.  Surviving blocks are rastered exactly.
         const int nl = min(s_nlarge, CT_LARGE_MAX);
+        const float* hz3 = a.hiz + kc.hiz_off[3];
+        const int hw3 = kc.hiz_w[3];
         for (int idx = warp; idx < nl; idx += CT_BLOCK / 32) {
           const int k = s_large[idx];
           const Setup s = load_setup(list + k);
           const int bx0 = max((int)(s.bbox & 255u), cx0), by0 = max((int)((s.bbox >> 8) & 255u), cy0);
           const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1), by1 = min((int)(s.bbox >> 24), cy1);
-          const int bw = bx1 - bx0 + 1, np = bw * (by1 - by0 + 1);
-          for (int i = lane; i < np; i += 32) raster_px(s, k, bx0 + i % bw, by0 + i / bw, rx0, ry0, a.depth0, s_z, &s_hits);
+          const int gbx0 = bx0 >> 3, gby0 = by0 >> 3;
+          const int nbx = (bx1 >> 3) - gbx0 + 1, nb = nbx * ((by1 >> 3) - gby0 + 1);
+          for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int b = b0 + lane;
+            bool keep = false;
+            if (b < nb) {
+              const int gx = gbx0 + b % nbx, gy = gby0 + b / nbx;
+              const int x0 = max(gx * 8, bx0), x1 = min(gx * 8 + 7, bx1);
+              const int y0 = max(gy * 8, by0), y1 = min(gy * 8 + 7, by1);
+              keep = block_may_hit(s, x0, x1, y0, y1, hz3[gy * hw3 + gx]);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, keep);
+            while (mask) {
+              const int bs = b0 + __ffs(mask) - 1;
+              mask &= mask - 1;
+              const int gx = gbx0 + bs % nbx, gy = gby0 + bs / nbx;
+              const int x0 = max(gx * 8, bx0), x1 = min(gx * 8 + 7, bx1);
+              const int y0 = max(gy * 8, by0), y1 = min(gy * 8 + 7, by1);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {  // 8x8 block = 2 pixels per lane
+                const int px = x0 + (lane & 7), py = y0 + (lane >> 3) + 4 * h;
+                if (px <= x1 && py <= y1) raster_px(s, k, px, py, rx0, ry0, a.depth0, s_z, &s_hits);
+              }
+            }
+          }
         }
         __syncthreads();
         if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
@@ -577,7 +671,9 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
         // --- shade hits, build the scaled difference image (0 where the gel is visible)
         for (int i = tid; i < REG * REG; i += CT_BLOCK) {
           const unsigned long long key = s_z[i];
-          float d[3] = {0.f, 0.f, 0.f};
+          float d[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) d[c] = 0.f;
           const int px = rx0 + i % REG, py = ry0 + i / REG;
           if (key != ZEMPTY) {
             const float t = __uint_as_float((uint32_t)(key >> 32));
@@ -599,33 +695,38 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
             n = normalize(n);
             V3 p{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
-            shade(p, n, rgb);
+            shade_t<NCH>(p, n, rgb);
             const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
+            for (int c = 0; c < NCH; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
             // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
             const int lx = px - tx, ly = py - ty;
             if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE && px <= wx1 && py <= wy1)
               gdep[py * TW + px] = sub(a.depth0[py * TW + px], t);
           }
-          s_diff[3 * i] = d[0]; s_diff[3 * i + 1] = d[1]; s_diff[3 * i + 2] = d[2];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) s_diff[NCH * i + c] = d[c];
         }
         __syncthreads();
         // --- 7-tap horizontal pass (BORDER_REFLECT_101 at the image edge)
         for (int i = tid; i < REG * TILE; i += CT_BLOCK) {
           const int ry = i / TILE, lx = i % TILE;
           const int px = tx + lx, py = ry0 + ry;
-          float acc[3] = {0.f, 0.f, 0.f};
+          float acc[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
           if (px < TW && py >= 0 && py < TH) {
 #pragma unroll
             for (int k = -3; k <= 3; ++k) {
               const int sx = reflect101(px + k, TW) - rx0;
               const float w = kc.gauss[k + 3];
-              const float* dp = &s_diff[(ry * REG + sx) * 3];
-              acc[0] = fmaf(w, dp[0], acc[0]); acc[1] = fmaf(w, dp[1], acc[1]); acc[2] = fmaf(w, dp[2], acc[2]);
+              const float* dp = &s_diff[(ry * REG + sx) * NCH];
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, dp[c], acc[c]);
             }
           }
-          s_h[3 * i] = acc[0]; s_h[3 * i + 1] = acc[1]; s_h[3 * i + 2] = acc[2];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) s_h[NCH * i + c] = acc[c];
         }
         __syncthreads();
         // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8))
@@ -633,18 +734,21 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
           const int ly = i / TILE, lx = i % TILE;
           const int px = tx + lx, py = ty + ly;
           if (px > wx1 || py > wy1) continue;
-          float acc[3] = {0.f, 0.f, 0.f};
+          float acc[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
 #pragma unroll
           for (int k = -3; k <= 3; ++k) {
             const int sy = reflect101(py + k, TH) - ry0;
             const float w = kc.gauss[k + 3];
-            const float* hp = &s_h[(sy * TILE + lx) * 3];
-            acc[0] = fmaf(w, hp[0], acc[0]); acc[1] = fmaf(w, hp[1], acc[1]); acc[2] = fmaf(w, hp[2], acc[2]);
+            const float* hp = &s_h[(sy * TILE + lx) * NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, hp[c], acc[c]);
           }
           const size_t o = ((size_t)py * TW + px) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float v = clampf(acc[c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
+            const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
             col[o + c] = (uint8_t)v;
           }
         }
@@ -731,6 +835,8 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
 // =============================================================================================
 // C-ABI
 // =============================================================================================
+static int g_gray = 0;  // mirrors kc.gray of the last igi_tactile_set_sensor (one device per process)
+
 extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
   IGI_REQUIRE(p != nullptr, "igi_tactile_set_sensor: null params");
   IGI_REQUIRE(p->width == TW && p->height == TH, "igi_tactile_set_sensor: only 224x224 is built");
@@ -753,6 +859,26 @@ extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
   for (int k = 0; k < 3; ++k) c.base[k] = p->base_color[k];
   c.metallic = p->metallic;
   c.roughness = p->roughness;
+  {
+    const float alpha = p->roughness * p->roughness;
+    c.sh_a2 = alpha * alpha;
+    float fmx = 0.f;
+    bool gray = true;
+    for (int k = 0; k < 3; ++k) {
+      c.sh_f0[k] = 0.04f * (1.0f - p->metallic) + p->base_color[k] * p->metallic;
+      c.sh_cdiff_pi[k] = p->base_color[k] * (1.0f - 0.04f) * (1.0f - p->metallic) * 0.31830988618379067f;
+      fmx = c.sh_f0[k] > fmx ? c.sh_f0[k] : fmx;
+      gray = gray && p->base_color[k] == p->base_color[0];
+    }
+    c.sh_f90 = fmx * 25.0f > 1.0f ? 1.0f : fmx * 25.0f;
+    for (int i = 0; i < p->n_lights; ++i)
+      for (int k = 0; k < 3; ++k) {
+        c.sh_rad[i][k] = p->light_col[3 * i + k] * p->light_int[i];
+        gray = gray && p->light_col[3 * i + k] == p->light_col[3 * i];
+      }
+    c.gray = gray ? 1 : 0;
+    g_gray = c.gray;
+  }
   for (int k = 0; k < 9; ++k) c.cam_R[k] = p->cam_R[k];
   for (int k = 0; k < 3; ++k) c.cam_p[k] = p->cam_p[k];
   c.gel_camx = (float)p->cam_p[0];
@@ -818,7 +944,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
   g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
-  g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz;
+  g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz; g.depth0 = st->depth0;
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
@@ -840,7 +966,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.counts = sc->counts; ca.bbox = sc->bbox;
   ca.worklist = sc->worklist; ca.work_n = sc->counters; ca.cursor = sc->counters + 1;
   ca.verts = m->verts; ca.vnorm = m->vnorm; ca.faces = m->faces;
-  ca.depth0 = st->depth0; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
+  ca.depth0 = st->depth0; ca.hiz = st->hiz; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
   ca.color = out->color; ca.gel_depth = out->gel_depth; ca.obs = out->obs;
   ca.obs_env_stride = out->obs_env_stride; ca.obs_sensor_stride = out->obs_sensor_stride;
   ca.sensors_per_env = fr->sensors_per_env;
@@ -850,7 +976,8 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = min(F, sms * 4);
   if (stages & 4) {
-    tac_contact<<<grid, CT_BLOCK, 0, s>>>(ca);
+    if (g_gray) tac_contact<1><<<grid, CT_BLOCK, 0, s>>>(ca);
+    else tac_contact<3><<<grid, CT_BLOCK, 0, s>>>(ca);
     IGI_CHECK_LAUNCH("tac_contact");
   }
   return IGI_OK;

@@ -134,3 +134,25 @@ def test_reference_style_handles(oracle_model, scene):
         assert np.array_equal(handles[e][n].bg_img, h.bg_img)
         tac = handles[e][n].remove_bg(color, handles[e][n].bg_img) * handles[e][n].mask
         assert tac.shape == (224, 224, 3)
+
+
+def test_coloured_lights_use_three_channel_path(built_lib, tmp_path):
+    """RGB lights (TACTO's default DIGIT look) take the 3-channel kernel instantiation."""
+    import yaml
+    from isaacgyminsertion_b200 import assets
+    from isaacgyminsertion_b200.allsight_render import BatchedAllSight
+    from oracle import tactile as ot
+    conf = yaml.safe_load(open(assets.SENSOR_YML))
+    conf["sensor"]["lights"]["colors"] = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    yml = tmp_path / "rgb.yml"
+    yml.write_text(yaml.safe_dump(conf))
+    model = ot.SensorModel(yml=str(yml))
+    assert len(np.unique(model.bg_sim.reshape(-1, 3), axis=0)) > 50
+    P = synthetic.tactile_poses(4, model.assets, seed=5)
+    eng = BatchedAllSight(4, P["mesh_id"], P["bg_id"], device="cuda:0", sensor_yml=str(yml))
+    _render(eng, P)
+    want = _oracle_frames(model, P)
+    for (e, n), w in want.items():
+        assert np.array_equal(eng.gel_depth[e, n].cpu().numpy(), w["gel_depth"])
+        assert np.abs(eng.color[e, n].cpu().numpy().astype(int) - w["color"].astype(int)).max() <= 1
+        assert np.abs(eng.obs[e, n].cpu().numpy() - w["obs"]).max() <= 1.0 / 255 + 1e-6
