@@ -20,7 +20,7 @@ namespace {
 constexpr int TW = 224, TH = 224;       // tactile image
 constexpr int OBS_W = 64, OBS_H = 32;   // encoder image after crop
 constexpr int MAX_LIGHTS = 8;
-constexpr int TILE = 32, HALO = 3, REG = TILE + 2 * HALO;  // contact tile + blur halo
+constexpr int HALO = 3;  // blur radius
 constexpr uint64_t ZEMPTY = 0xffffffffffffffffull;
 
 struct TacConst {
@@ -129,8 +129,7 @@ __device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
 }
 
 // coverage + depth of one pixel; returns t (depth) or -1 when not covered / clipped
-__device__ __forceinline__ float cover(const Setup& s, int px, int py, float& e1, float& e2, float& esum) {
-  const float dx = k_dxp[px], dy = k_dyp[py];
+__device__ __forceinline__ float cover(const Setup& s, float dx, float dy, float& e1, float& e2, float& esum) {
   const float e0 = edge_fn(dx, dy, s.n0);
   if (!edge_in(e0, s.n0)) return -1.0f;
   e1 = edge_fn(dx, dy, s.n1);
@@ -240,7 +239,7 @@ __global__ void tac_gel_raster(const float* __restrict__ gel_tris, int G, unsign
   for (int py = y0; py <= y1; ++py)
     for (int px = x0; px <= x1; ++px) {
       float e1, e2, es;
-      const float tt = cover(s, px, py, e1, e2, es);
+      const float tt = cover(s, k_dxp[px], k_dyp[py], e1, e2, es);
       if (tt < 0.0f) continue;
       const unsigned long long key = ((unsigned long long)__float_as_uint(tt) << 32) | (uint32_t)g;
       atomicMin(zbuf + (size_t)py * TW + px, key);
@@ -427,7 +426,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
         for (int py = y0; py <= y1 && !vis; ++py)
           for (int px = x0; px <= x1; ++px) {
             float e1, e2, es;
-            const float t = cover(s, px, py, e1, e2, es);
+            const float t = cover(s, k_dxp[px], k_dyp[py], e1, e2, es);
             if (t < 0.0f) continue;
             const float d0 = __ldg(a.depth0 + py * TW + px);
             if (d0 == 0.0f || t < d0) { vis = true; break; }
@@ -534,15 +533,16 @@ struct ContactArgs {
   int kmax;
 };
 constexpr int CT_BLOCK = 256;
+constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
+constexpr int CT_BUD_GRAY = 8192;    // region pixels (interior + halo) held in shared memory, 8 B each
+constexpr int CT_BUD_RGB = 4096;     // three-channel path: + 24 B per pixel of difference / blur planes
+constexpr int CT_COOP_SPAN = 24;     // row spans longer than this are rastered by the whole warp
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * n - 2 - i;
   return i;
 }
-
-constexpr int CT_LARGE_AREA = 48;   // bbox area (px) above which a triangle is rastered by a whole warp
-constexpr int CT_LARGE_MAX = 1024;
 
 __device__ __forceinline__ Setup load_setup(const Setup* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -551,16 +551,40 @@ __device__ __forceinline__ Setup load_setup(const Setup* p) {
   return u.s;
 }
 
-__device__ __forceinline__ void raster_px(const Setup& s, int k, int px, int py, int rx0, int ry0,
-                                          const float* __restrict__ depth0, unsigned long long* s_z, int* s_hits) {
+// Conservative pixel-column interval [xlo, xhi] of row `dy` that can lie inside the three edge planes.
+// An edge value is affine in the ray slope dx: e = dx*n.x + (dy*n.y - n.z); the bound -c/n.x is widened
+// by the worst-case rounding of the exactly-rounded per-pixel evaluation in cover(), then mapped to
+// pixel columns.  Only a superset is needed: every pixel of the interval still runs cover().
+__device__ __forceinline__ void row_span(const Setup& s, float dy, float sx0, float kx, int bx0, int bx1, int& xlo, int& xhi) {
+  float L = -1e30f, U = 1e30f;
+  bool empty = false;
+  auto edge = [&](V3 n) {
+    const float cy = dy * n.y;
+    const float c = cy - n.z;
+    const float eps = 2e-6f * (1.7f * fabsf(n.x) + fabsf(cy) + fabsf(n.z));
+    if (n.x == 0.0f) {
+      empty = empty || (c > eps);
+    } else {
+      const float inv = 1.0f / n.x;
+      const float b = -c * inv, m = eps * fabsf(inv);
+      if (n.x > 0.0f) U = fminf(U, b + m); else L = fmaxf(L, b - m);
+    }
+  };
+  edge(s.n0); edge(s.n1); edge(s.n2);
+  const float pl = fmaxf((L - sx0) * kx - 0.02f, -1.0f), pu = fminf((U - sx0) * kx + 0.02f, (float)TW);
+  xlo = max(bx0, (int)ceilf(pl));
+  xhi = empty ? -1 : min(bx1, (int)floorf(pu));
+}
+
+// One fragment: exact coverage + depth, GL_LESS against what the shared z-buffer holds (it starts
+// as the gel depth, so a peg fragment only lands where it is in front of the gel).
+// key = depth bits << 32 | (orig face << 12 | slot) + 1; the gel's key has a zero low word.
+__device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, float dy, unsigned long long* zp, int* s_hits) {
   float e1, e2, es;
-  const float t = cover(s, px, py, e1, e2, es);
+  const float t = cover(s, dx, dy, e1, e2, es);
   if (t < 0.0f) return;
-  const float d0 = __ldg(depth0 + py * TW + px);
-  if (d0 != 0.0f && !(t < d0)) return;  // GL_LESS against the gel
   const unsigned long long key =
-      ((unsigned long long)__float_as_uint(t) << 32) | ((unsigned long long)s.orig << 12) | (uint32_t)k;
-  unsigned long long* zp = &s_z[(py - ry0) * REG + (px - rx0)];
+      ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)((((uint32_t)s.orig << 12) | (uint32_t)k) + 1u);
   if (key < *zp) {
     atomicMin(zp, key);
     *s_hits = 1;
@@ -568,15 +592,25 @@ __device__ __forceinline__ void raster_px(const Setup& s, int k, int px, int py,
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
-  __shared__ unsigned long long s_z[REG * REG];   // depth<<32 | orig<<12 | slot
-  __shared__ float s_diff[REG * REG * NCH];       // (c - bg_sim) * scale
-  __shared__ float s_h[REG * TILE * NCH];         // horizontal blur
+__global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(ContactArgs a) {
+  constexpr int BUD = NCH == 1 ? CT_BUD_GRAY : CT_BUD_RGB;
+  constexpr int DS = NCH == 1 ? 2 : 3;  // float stride between pixels of the difference / blur planes
+  extern __shared__ __align__(16) unsigned char ct_smem[];
+  // z-buffer (8 B / pixel).  Gray path: once a pixel is shaded its key is dead, and the two words
+  // are reused as (difference, horizontal blur) so the whole pipeline lives in 8 B per pixel.
+  unsigned long long* s_z = reinterpret_cast<unsigned long long*>(ct_smem);
+  float* s_diff = NCH == 1 ? reinterpret_cast<float*>(ct_smem) : reinterpret_cast<float*>(ct_smem + (size_t)BUD * 8);
+  float* s_h = NCH == 1 ? s_diff + 1 : s_diff + (size_t)BUD * 3;
+  __shared__ int s_off[CT_CHUNK];
+  __shared__ int s_wsum[CT_BLOCK / 32];
   __shared__ float sM[12];
-  __shared__ int s_large[CT_LARGE_MAX];
-  __shared__ int s_nlarge, s_hits, s_frame;
-  __shared__ int s_hb[4];                         // bounds of the tiles that produced hits
+  __shared__ int s_hits, s_frame;
+  __shared__ int s_hb[4];  // bounds of the pixels that changed (hits dilated by the blur radius)
+  __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = CT_BLOCK / 32;
+  for (int i = tid; i < TW; i += CT_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
+  const float span_x0 = k_dxp[0], span_kx = (float)(TW - 1) / (k_dxp[TW - 1] - k_dxp[0]);
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -590,174 +624,238 @@ __global__ void __launch_bounds__(CT_BLOCK) tac_contact(ContactArgs a) {
     if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const int K = a.counts[f];
     const Setup* list = a.setups + (size_t)f * a.kmax;
-    // candidate window: union of the triangle boxes, dilated by the blur radius
+    // window that can change: union of the triangle boxes, dilated by the blur radius
     const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
     const int wx1 = min(a.bbox[4 * f + 2] + HALO, TW - 1), wy1 = min(a.bbox[4 * f + 3] + HALO, TH - 1);
     const uint8_t* bgr = a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3;
     uint8_t* col = a.color + (size_t)f * TW * TH * 3;
     float* gdep = a.gel_depth + (size_t)f * TW * TH;
+    // cut the window into the fewest sub-windows whose region (interior + halo) fits the budget
+    const int ww = wx1 - wx0 + 1, wh = wy1 - wy0 + 1;
+    int nsx = 1, nsy = 1;
+    while (((ww + nsx - 1) / nsx + 2 * HALO) * ((wh + nsy - 1) / nsy + 2 * HALO) > BUD) {
+      if ((ww + nsx - 1) / nsx >= (wh + nsy - 1) / nsy) ++nsx; else ++nsy;
+    }
+    const int tw = (ww + nsx - 1) / nsx, th = (wh + nsy - 1) / nsy;
+    const int RW = tw + 2 * HALO, RH = th + 2 * HALO;
 
-    for (int ty = wy0; ty <= wy1; ty += TILE)
-      for (int tx = wx0; tx <= wx1; tx += TILE) {
-        // region = tile + halo, image coordinates [rx0, rx0+REG) x [ry0, ry0+REG)
+    for (int ty = wy0; ty <= wy1; ty += th)
+      for (int tx = wx0; tx <= wx1; tx += tw) {
+        // interior [tx, ix1] x [ty, iy1]; region = interior + halo at image coordinates rx0.., ry0..
+        const int ix1 = min(tx + tw - 1, wx1), iy1 = min(ty + th - 1, wy1);
         const int rx0 = tx - HALO, ry0 = ty - HALO;
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
-        const int cx1 = min(rx0 + REG - 1, TW - 1), cy1 = min(ry0 + REG - 1, TH - 1);
+        const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
         __syncthreads();
-        for (int i = tid; i < REG * REG; i += CT_BLOCK) s_z[i] = ZEMPTY;
-        if (tid == 0) { s_nlarge = 0; s_hits = 0; }
-        __syncthreads();
-        // --- pass A: one thread per small triangle; large ones are queued for pass B
-        for (int k = tid; k < K; k += CT_BLOCK) {
-          const uint32_t bb = __ldg(&list[k].bbox);
-          const int bx0 = max((int)(bb & 255u), cx0), by0 = max((int)((bb >> 8) & 255u), cy0);
-          const int bx1 = min((int)((bb >> 16) & 255u), cx1), by1 = min((int)(bb >> 24), cy1);
-          if (bx0 > bx1 || by0 > by1) continue;
-          if ((bx1 - bx0 + 1) * (by1 - by0 + 1) > CT_LARGE_AREA) {
-            const int slot = atomicAdd(&s_nlarge, 1);
-            if (slot < CT_LARGE_MAX) { s_large[slot] = k; continue; }
-          }
-          const Setup s = load_setup(list + k);
-          for (int py = by0; py <= by1; ++py)
-            for (int px = bx0; px <= bx1; ++px) raster_px(s, k, px, py, rx0, ry0, a.depth0, s_z, &s_hits);
-        }
-        __syncthreads();
-        // --- pass B: one warp per large triangle.  Its clipped box is cut into image-aligned 8x8
-        // blocks; a block is dropped when it lies outside an edge plane or when the nearest depth
-        // of the triangle's plane over the block is behind the farthest gel depth of the block
-        // (level 3 of the depth0 max-pyramid).  Both bounds are affine in the ray slopes, so the
-        // extreme over a block sits at a corner; a relative margin keeps them conservative against
-        // the separately-rounded per-pixel arithmetic.  Surviving blocks are rastered exactly.
-        const int nl = min(s_nlarge, CT_LARGE_MAX);
-        const float* hz3 = a.hiz + kc.hiz_off[3];
-        const int hw3 = kc.hiz_w[3];
-        for (int idx = warp; idx < nl; idx += CT_BLOCK / 32) {
-          const int k = s_large[idx];
-          const Setup s = load_setup(list + k);
-          const int bx0 = max((int)(s.bbox & 255u), cx0), by0 = max((int)((s.bbox >> 8) & 255u), cy0);
-          const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1), by1 = min((int)(s.bbox >> 24), cy1);
-          const int gbx0 = bx0 >> 3, gby0 = by0 >> 3;
-          const int nbx = (bx1 >> 3) - gbx0 + 1, nb = nbx * ((by1 >> 3) - gby0 + 1);
-          for (int b0 = 0; b0 < nb; b0 += 32) {
-            const int b = b0 + lane;
-            bool keep = false;
-            if (b < nb) {
-              const int gx = gbx0 + b % nbx, gy = gby0 + b / nbx;
-              const int x0 = max(gx * 8, bx0), x1 = min(gx * 8 + 7, bx1);
-              const int y0 = max(gy * 8, by0), y1 = min(gy * 8 + 7, by1);
-              keep = block_may_hit(s, x0, x1, y0, y1, hz3[gy * hw3 + gx]);
+        // --- z-buffer starts as the gel
+        for (int ry = warp; ry < RH; ry += NW) {
+          const int py = ry0 + ry;
+          for (int rx = lane; rx < RW; rx += 32) {
+            const int px = rx0 + rx;
+            unsigned long long key = ZEMPTY;
+            if (px >= cx0 && px <= cx1 && py >= cy0 && py <= cy1) {
+              const float d0 = __ldg(a.depth0 + py * TW + px);
+              if (d0 != 0.0f) key = (unsigned long long)__float_as_uint(d0) << 32;
             }
-            unsigned mask = __ballot_sync(0xffffffffu, keep);
-            while (mask) {
-              const int bs = b0 + __ffs(mask) - 1;
-              mask &= mask - 1;
-              const int gx = gbx0 + bs % nbx, gy = gby0 + bs / nbx;
-              const int x0 = max(gx * 8, bx0), x1 = min(gx * 8 + 7, bx1);
-              const int y0 = max(gy * 8, by0), y1 = min(gy * 8 + 7, by1);
+            s_z[ry * RW + rx] = key;
+          }
+        }
+        if (tid == 0) s_hits = 0;
+        // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
+        // every thread gets the same number of rows whatever the triangle sizes are
+        for (int c0 = 0; c0 < K; c0 += CT_CHUNK) {
+          const int kn = min(CT_CHUNK, K - c0);
+          int rows[CT_CHUNK / CT_BLOCK], sum = 0;
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {  // 8x8 block = 2 pixels per lane
-                const int px = x0 + (lane & 7), py = y0 + (lane >> 3) + 4 * h;
-                if (px <= x1 && py <= y1) raster_px(s, k, px, py, rx0, ry0, a.depth0, s_z, &s_hits);
+          for (int j = 0; j < CT_CHUNK / CT_BLOCK; ++j) {
+            const int k = tid * (CT_CHUNK / CT_BLOCK) + j;
+            rows[j] = 0;
+            if (k < kn) {
+              const uint32_t bb = __ldg(&list[c0 + k].bbox);
+              const int bx0 = max((int)(bb & 255u), cx0), by0 = max((int)((bb >> 8) & 255u), cy0);
+              const int bx1 = min((int)((bb >> 16) & 255u), cx1), by1 = min((int)(bb >> 24), cy1);
+              if (bx0 <= bx1 && by0 <= by1) rows[j] = by1 - by0 + 1;
+            }
+            sum += rows[j];
+          }
+          int incl = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+          }
+          __syncthreads();  // previous chunk's readers of s_off / s_wsum are done; z init visible
+          if (lane == 31) s_wsum[warp] = incl;
+          __syncthreads();
+          int woff = 0, total = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            const int t = s_wsum[w];
+            if (w < warp) woff += t;
+            total += t;
+          }
+          int base = woff + incl - sum;
+#pragma unroll
+          for (int j = 0; j < CT_CHUNK / CT_BLOCK; ++j) {
+            s_off[tid * (CT_CHUNK / CT_BLOCK) + j] = base;
+            base += rows[j];
+          }
+          __syncthreads();
+          for (int i0 = warp * 32; i0 < total; i0 += CT_BLOCK) {
+            const int i = i0 + lane;
+            int k = 0, py = 0, xlo = 0, xhi = -1;
+            Setup s;
+            if (i < total) {
+              int lo = 0, hi = kn - 1;
+              while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
               }
+              k = c0 + lo;
+              s = load_setup(list + k);
+              const int bx0 = max((int)(s.bbox & 255u), cx0), by0 = max((int)((s.bbox >> 8) & 255u), cy0);
+              const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1);
+              py = by0 + (i - s_off[lo]);
+              row_span(s, s_dyp[py], span_x0, span_kx, bx0, bx1, xlo, xhi);
+            }
+            // long spans: the whole warp takes them, one pixel per lane
+            unsigned big = __ballot_sync(0xffffffffu, xhi - xlo + 1 > CT_COOP_SPAN);
+            while (big) {
+              const int src = __ffs(big) - 1;
+              big &= big - 1;
+              const int kk = __shfl_sync(0xffffffffu, k, src), yy = __shfl_sync(0xffffffffu, py, src);
+              const int xa = __shfl_sync(0xffffffffu, xlo, src), xb = __shfl_sync(0xffffffffu, xhi, src);
+              const Setup ss = load_setup(list + kk);
+              unsigned long long* zrow = s_z + (yy - ry0) * RW - rx0;
+              const float dyy = s_dyp[yy];
+              for (int px = xa + lane; px <= xb; px += 32) raster_frag(ss, kk, s_dxp[px], dyy, zrow + px, &s_hits);
+              if (lane == src) xhi = -1;
+            }
+            if (xlo <= xhi) {
+              unsigned long long* zrow = s_z + (py - ry0) * RW - rx0;
+              const float dy = s_dyp[py];
+              for (int px = xlo; px <= xhi; ++px) raster_frag(s, k, s_dxp[px], dy, zrow + px, &s_hits);
             }
           }
         }
         __syncthreads();
         if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
-        if (tid == 0) {
-          s_hb[0] = min(s_hb[0], cx0); s_hb[1] = min(s_hb[1], cy0);
-          s_hb[2] = max(s_hb[2], cx1); s_hb[3] = max(s_hb[3], cy1);
-        }
         // --- shade hits, build the scaled difference image (0 where the gel is visible)
-        for (int i = tid; i < REG * REG; i += CT_BLOCK) {
-          const unsigned long long key = s_z[i];
-          float d[NCH];
+        for (int ry = warp; ry < RH; ry += NW) {
+          const int py = ry0 + ry;
+          bool rowhit = false;
+          int hx0 = TW, hx1 = -1;
+          for (int rx = lane; rx < RW; rx += 32) {
+            const int px = rx0 + rx;
+            const int i = ry * RW + rx;
+            const unsigned long long key = s_z[i];
+            const uint32_t low = (uint32_t)key;
+            float d[NCH];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) d[c] = 0.f;
-          const int px = rx0 + i % REG, py = ry0 + i / REG;
-          if (key != ZEMPTY) {
-            const float t = __uint_as_float((uint32_t)(key >> 32));
-            const Setup s = load_setup(list + (int)(key & 0xfffu));
-            const float dx = k_dxp[px], dy = k_dyp[py];
-            const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
-            const float es = add(add(e0, e1), e2);
-            const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
-            const float l0 = sub(sub(1.0f, l1), l2);
-            const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
-            float no[3];
+            for (int c = 0; c < NCH; ++c) d[c] = 0.f;
+            const bool hit = key != ZEMPTY && low != 0u;
+            if (hit) {
+              const float t = __uint_as_float((uint32_t)(key >> 32));
+              const Setup s = load_setup(list + (int)((low - 1u) & 0xfffu));
+              const float dx = s_dxp[px], dy = s_dyp[py];
+              const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
+              const float es = add(add(e0, e1), e2);
+              const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
+              const float l0 = sub(sub(1.0f, l1), l2);
+              const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
+              float no[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
-            V3 n;
-            n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
-            n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
-            n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
-            n = normalize(n);
-            V3 p{mul(dx, t), mul(dy, t), -t};
-            uint8_t rgb[3];
-            shade_t<NCH>(p, n, rgb);
-            const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
+              for (int c = 0; c < 3; ++c)
+                no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
+              V3 n;
+              n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
+              n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
+              n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
+              n = normalize(n);
+              V3 p{mul(dx, t), mul(dy, t), -t};
+              uint8_t rgb[3];
+              shade_t<NCH>(p, n, rgb);
+              const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
-            // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
-            const int lx = px - tx, ly = py - ty;
-            if (lx >= 0 && lx < TILE && ly >= 0 && ly < TILE && px <= wx1 && py <= wy1)
-              gdep[py * TW + px] = sub(a.depth0[py * TW + px], t);
+              for (int c = 0; c < NCH; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
+              // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
+              if (px >= tx && px <= ix1 && py >= ty && py <= iy1)
+                gdep[py * TW + px] = sub(__ldg(a.depth0 + py * TW + px), t);
+              rowhit = true;
+              hx0 = min(hx0, px); hx1 = max(hx1, px);
+            }
+            if (NCH == 1) {
+              s_diff[DS * i] = d[0];
+            } else {
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = d[c];
+            }
           }
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) s_diff[NCH * i + c] = d[c];
+          if (__any_sync(0xffffffffu, rowhit)) {
+            hx0 = __reduce_min_sync(0xffffffffu, hx0);
+            hx1 = __reduce_max_sync(0xffffffffu, hx1);
+            if (lane == 0) {
+              atomicMin(&s_hb[0], hx0); atomicMax(&s_hb[2], hx1);
+              atomicMin(&s_hb[1], py); atomicMax(&s_hb[3], py);
+            }
+          }
         }
         __syncthreads();
-        // --- 7-tap horizontal pass (BORDER_REFLECT_101 at the image edge)
-        for (int i = tid; i < REG * TILE; i += CT_BLOCK) {
-          const int ry = i / TILE, lx = i % TILE;
-          const int px = tx + lx, py = ry0 + ry;
-          float acc[NCH];
+        // --- 7-tap horizontal pass over the interior columns (BORDER_REFLECT_101 at the image edge)
+        const int iw = ix1 - tx + 1;
+        for (int ry = warp; ry < RH; ry += NW) {
+          const int py = ry0 + ry;
+          if (py < 0 || py >= TH) continue;
+          for (int lx = lane; lx < iw; lx += 32) {
+            const int px = tx + lx;
+            float acc[NCH];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
-          if (px < TW && py >= 0 && py < TH) {
+            for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
 #pragma unroll
             for (int k = -3; k <= 3; ++k) {
               const int sx = reflect101(px + k, TW) - rx0;
               const float w = kc.gauss[k + 3];
-              const float* dp = &s_diff[(ry * REG + sx) * NCH];
+              const float* dp = &s_diff[(ry * RW + sx) * DS];
 #pragma unroll
               for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, dp[c], acc[c]);
             }
-          }
+            float* hp = &s_h[(ry * RW + (px - rx0)) * DS];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) s_h[NCH * i + c] = acc[c];
+            for (int c = 0; c < NCH; ++c) hp[c] = acc[c];
+          }
         }
         __syncthreads();
         // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8))
-        for (int i = tid; i < TILE * TILE; i += CT_BLOCK) {
-          const int ly = i / TILE, lx = i % TILE;
-          const int px = tx + lx, py = ty + ly;
-          if (px > wx1 || py > wy1) continue;
-          float acc[NCH];
+        for (int ly = warp; ly <= iy1 - ty; ly += NW) {
+          const int py = ty + ly;
+          for (int lx = lane; lx < iw; lx += 32) {
+            const int px = tx + lx;
+            float acc[NCH];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+            for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
 #pragma unroll
-          for (int k = -3; k <= 3; ++k) {
-            const int sy = reflect101(py + k, TH) - ry0;
-            const float w = kc.gauss[k + 3];
-            const float* hp = &s_h[(sy * TILE + lx) * NCH];
+            for (int k = -3; k <= 3; ++k) {
+              const int sy = reflect101(py + k, TH) - ry0;
+              const float w = kc.gauss[k + 3];
+              const float* hp = &s_h[(sy * RW + (px - rx0)) * DS];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, hp[c], acc[c]);
-          }
-          const size_t o = ((size_t)py * TW + px) * 3;
+              for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, hp[c], acc[c]);
+            }
+            const size_t o = ((size_t)py * TW + px) * 3;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
-            col[o + c] = (uint8_t)v;
+            for (int c = 0; c < 3; ++c) {
+              const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
+              col[o + c] = (uint8_t)v;
+            }
           }
         }
       }
     __syncthreads();
-    // --- obs pixels whose 3.5x3.5 source window meets a tile that changed -----------------------
+    // --- obs pixels whose 3.5x3.5 source window meets a pixel that changed ---------------------
     // flipud + crop: obs row r reads flipped rows [3.5r, 3.5r+3.5) = original rows 223 - that.
     if (s_hb[2] >= 0) {
-      const int hx0 = s_hb[0], hy0 = s_hb[1], hx1 = s_hb[2], hy1 = s_hb[3];
+      const int hx0 = max(s_hb[0] - HALO, 0), hy0 = max(s_hb[1] - HALO, 0);
+      const int hx1 = min(s_hb[2] + HALO, TW - 1), hy1 = min(s_hb[3] + HALO, TH - 1);
       const int fy_lo = TH - 1 - hy1, fy_hi = TH - 1 - hy0;  // changed rows in flipped coordinates
       const int oy0 = max((2 * fy_lo) / 7 - 1, 0), oy1 = min((2 * fy_hi) / 7 + 1, OBS_H - 1);
       const int ox0 = max((2 * hx0) / 7 - 1, 0), ox1 = min((2 * hx1) / 7 + 1, OBS_W - 1);
@@ -974,10 +1072,16 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = min(F, sms * 4);
   if (stages & 4) {
-    if (g_gray) tac_contact<1><<<grid, CT_BLOCK, 0, s>>>(ca);
-    else tac_contact<3><<<grid, CT_BLOCK, 0, s>>>(ca);
+    constexpr size_t smem_gray = (size_t)CT_BUD_GRAY * 8, smem_rgb = (size_t)CT_BUD_RGB * (8 + 24);
+    static bool attr_set = false;
+    if (!attr_set) {
+      IGI_CUDA(cudaFuncSetAttribute(tac_contact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gray));
+      IGI_CUDA(cudaFuncSetAttribute(tac_contact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rgb));
+      attr_set = true;
+    }
+    if (g_gray) tac_contact<1><<<min(F, sms * 3), CT_BLOCK, smem_gray, s>>>(ca);
+    else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(ca);
     IGI_CHECK_LAUNCH("tac_contact");
   }
   return IGI_OK;
