@@ -37,7 +37,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    extra = os.environ.get("IGI_NVCC_EXTRA", "").split()   # e.g. -DGEOM_VIS_TEST=0 for tuning experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -83,6 +83,21 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   const int hi = min(lo + chunk, npix);
   const int lane = tid & 31, warp = tid >> 5;
 
+  // A masked-out pixel with finite depth becomes d = +-0 (pcl_utils.py / task :956-959) and maps to the
+  // camera centre whatever its (u, v): w = ext[3,:], o = w @ e2g_inv^T.  Signs of zero do not change
+  // the inclusive box test, so unless that one point is inside the box (it never is for the Factory
+  // camera, x = 0.731 > 0.7) every masked-out pixel can be skipped without evaluating it; a
+  // masked-out miss (-inf * 0 = NaN) is dropped by `d > -depth_max` either way.
+  bool zero_kept = true;
+  if (g_seg && p.has_box) {
+    float o[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o[j] = fmaf(A[15], B[4 * j + 3], fmaf(A[14], B[4 * j + 2], fmaf(A[13], B[4 * j + 1], A[12] * B[4 * j])));
+    zero_kept = (o[0] >= p.box[0]) && (o[0] <= p.box[1]) && (o[1] >= p.box[2]) && (o[1] <= p.box[3]) &&
+                (o[2] >= p.box[4]) && (o[2] <= p.box[5]);
+  }
+
   for (int c = 0; c < p.n_classes; ++c) {
     const int sid = p.seg_ids[c];
     // pass 1: count kept pixels of this thread's chunk; pass 2: write them.
@@ -95,7 +110,11 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
       int slot = base;
       for (int i = lo; i < hi; ++i) {
         float d = s_depth[i];
-        if (g_seg) d = __fmul_rn(d, (s_seg[i] == sid) ? 1.0f : 0.0f);  // -inf*0 = NaN, finite*0 = -0
+        if (g_seg) {
+          const bool mine = s_seg[i] == sid;
+          if (!mine && !zero_kept) continue;
+          d = __fmul_rn(d, mine ? 1.0f : 0.0f);  // -inf*0 = NaN, finite*0 = -0
+        }
         bool ok = (p.depth_max < 0.0f) ? true : (d > -p.depth_max);
         if (!ok) continue;
         const int v = i / p.W, u = i - v * p.W;
@@ -237,98 +256,163 @@ struct FpsCand {
 
 __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_t task_stride,
                                                         const int32_t* count, const int32_t* any,
-                                                        int64_t count_stride, int n_fixed, int m,
+                                                        int64_t count_stride, int n_fixed, int n_tasks, int m,
                                                         float* out_pts, int64_t out_stride, int32_t* out_idx,
                                                         int min_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int task = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = count ? count[(size_t)task * count_stride] : n_fixed;
-  if (n < min_n) return;  // small tasks belong to fps_warp_kernel
-  const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
-  float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
-  int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
-  if (!live) {
-    for (int i = tid; i < m; i += kFpsBlock) {
-      if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
-      if (idst) idst[i] = 0;
-    }
-    return;
-  }
-  // smem: x[n] y[n] z[n] temp[n] (cap = n rounded up), then m selected ids
-  const int cap = (n + 3) & ~3;
-  float* sx = reinterpret_cast<float*>(smem_raw);
-  float* sy = sx + cap;
-  float* sz = sy + cap;
-  float* st = sz + cap;
   __shared__ FpsCand s_cand[2][kFpsBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // persistent CTAs stride over the tasks; tasks below min_n belong to fps_warp_kernel
+  for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int n = count ? count[(size_t)task * count_stride] : n_fixed;
+    if (n < min_n) continue;
+    const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
+    float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
+    int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
+    if (!live) {
+      for (int i = tid; i < m; i += kFpsBlock) {
+        if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
+        if (idst) idst[i] = 0;
+      }
+      continue;
+    }
+    // smem: x[n] y[n] z[n] temp[n] (cap = n rounded up)
+    const int cap = (n + 3) & ~3;
+    float* sx = reinterpret_cast<float*>(smem_raw);
+    float* sy = sx + cap;
+    float* sz = sy + cap;
+    float* st = sz + cap;
+    __syncthreads();  // previous task's readers are done with the arrays
+    const float* src = pts + (size_t)task * task_stride;
+    for (int k = tid; k < n; k += kFpsBlock) {
+      sx[k] = src[(size_t)k * 3 + 0];
+      sy[k] = src[(size_t)k * 3 + 1];
+      sz[k] = src[(size_t)k * 3 + 2];
+      st[k] = 1e10f;
+    }
+    // upstream block size: largest power of two <= min(n, 512)
+    int lg = 31 - __clz(n);
+    if (lg > 9) lg = 9;
+    const uint32_t bmask = (1u << lg) - 1u;
+    __syncthreads();
 
-  const float* src = pts + (size_t)task * task_stride;
-  for (int k = tid; k < n; k += kFpsBlock) {
-    sx[k] = src[(size_t)k * 3 + 0];
-    sy[k] = src[(size_t)k * 3 + 1];
-    sz[k] = src[(size_t)k * 3 + 2];
-    st[k] = 1e10f;
+    int old = 0;
+    if (tid == 0) {
+      if (idst) idst[0] = 0;
+      if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
+    }
+    int j = 1;
+    for (; j < m; ++j) {
+      const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+      uint32_t bhi = 0, blo = 0;
+      for (int k = tid; k < n; k += kFpsBlock) {
+        const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
+        const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+        if (mag <= 1e-3f) continue;
+        const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d2 = fminf(d, st[k]);
+        st[k] = d2;
+        const uint32_t hi = __float_as_uint(d2) + 1u;
+        const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
+        const uint32_t lo = ~((rev << 16) | (uint32_t)k);
+        if (hi > bhi || (hi == bhi && lo > blo)) { bhi = hi; blo = lo; }
+      }
+      // warp arg-max with two REDUX passes
+      const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
+      const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
+      if (lane == 0) { s_cand[j & 1][warp].hi = whi; s_cand[j & 1][warp].lo = wlo; }
+      __syncthreads();
+      uint32_t fhi = 0, flo = 0;
+#pragma unroll
+      for (int wi = 0; wi < kFpsBlock / 32; ++wi) {
+        const FpsCand c = s_cand[j & 1][wi];
+        if (c.hi > fhi || (c.hi == fhi && c.lo > flo)) { fhi = c.hi; flo = c.lo; }
+      }
+      old = (fhi == 0) ? 0 : (int)((~flo) & 0xffffu);
+      if (tid == 0) {
+        if (idst) idst[j] = old;
+        if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
+      }
+      // Every remaining distance is 0 (or there is no candidate): the running minima can no longer
+      // change, so every later pick is this same index.
+      if (fhi <= 1u) { ++j; break; }
+    }
+    for (int i = j + tid; i < m; i += kFpsBlock) {
+      if (idst) idst[i] = old;
+      if (dst) { dst[i * 3 + 0] = sx[old]; dst[i * 3 + 1] = sy[old]; dst[i * 3 + 2] = sz[old]; }
+    }
   }
-  // upstream block size: largest power of two <= min(n, 512)
+}
+
+// The m-1 dependent picks of one warp-resident task with PPL points per lane (n <= 32*PPL).
+// Returns after filling sel[0..m).  Once the winning distance is 0 (all points already picked, or
+// only duplicates left) or nothing is a candidate, the minima cannot change any more and every
+// later pick repeats the same index, so the loop stops there and the tail is filled directly.
+template <int PPL>
+__device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy, const float* sz, int n, int m,
+                                              int lane, unsigned short* sel) {
   int lg = 31 - __clz(n);
   if (lg > 9) lg = 9;
   const uint32_t bmask = (1u << lg) - 1u;
-  __syncthreads();
-
-  int old = 0;
-  if (tid == 0) {
-    if (idst) idst[0] = 0;
-    if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
-  }
-  for (int j = 1; j < m; ++j) {
-    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-    uint32_t bhi = 0, blo = 0;
-    for (int k = tid; k < n; k += kFpsBlock) {
+  float temp[PPL];
+  uint32_t lokey[PPL];  // 0 = not a candidate
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const int k = lane + 32 * i;
+    temp[i] = 1e10f;
+    lokey[i] = 0u;
+    if (k < n) {
       const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
       const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
-      if (mag <= 1e-3f) continue;
-      const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const float d2 = fminf(d, st[k]);
-      st[k] = d2;
-      const uint32_t hi = __float_as_uint(d2) + 1u;
-      const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
-      const uint32_t lo = ~((rev << 16) | (uint32_t)k);
-      if (hi > bhi || (hi == bhi && lo > blo)) { bhi = hi; blo = lo; }
-    }
-    // warp arg-max with two REDUX passes
-    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
-    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
-    if (lane == 0) { s_cand[j & 1][warp].hi = whi; s_cand[j & 1][warp].lo = wlo; }
-    __syncthreads();
-    uint32_t fhi = 0, flo = 0;
-#pragma unroll
-    for (int wi = 0; wi < kFpsBlock / 32; ++wi) {
-      const FpsCand c = s_cand[j & 1][wi];
-      if (c.hi > fhi || (c.hi == fhi && c.lo > flo)) { fhi = c.hi; flo = c.lo; }
-    }
-    old = (fhi == 0) ? 0 : (int)((~flo) & 0xffffu);
-    if (tid == 0) {
-      if (idst) idst[j] = old;
-      if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
+      if (mag > 1e-3f) {
+        const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
+        lokey[i] = ~((rev << 16) | (uint32_t)k);
+      }
     }
   }
+  int old = 0;
+  if (lane == 0) sel[0] = 0;
+  int j = 1;
+  for (; j < m; ++j) {
+    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    uint32_t bhi = 0, blo = 0;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (lokey[i] != 0u) {
+        const int k = lane + 32 * i;
+        const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d2 = fminf(d, temp[i]);
+        temp[i] = d2;
+        const uint32_t hi = __float_as_uint(d2) + 1u;
+        if (hi > bhi || (hi == bhi && lokey[i] > blo)) { bhi = hi; blo = lokey[i]; }
+      }
+    }
+    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
+    old = (whi == 0) ? 0 : (int)((~wlo) & 0xffffu);
+    if (lane == 0) sel[j] = (unsigned short)old;
+    if (whi <= 1u) { ++j; break; }
+  }
+  for (int i = j + lane; i < m; i += 32) sel[i] = (unsigned short)old;
 }
 
 // Warp-per-task FPS for the common small clouds (n <= FW_MAXN): the task's points sit in a
 // per-warp SoA slice of shared memory, running minimum distances and tie keys in registers,
 // the arg-max is two REDUX instructions, no block barrier anywhere.  Same selection rule as
 // fps_kernel (and oracle/fps.py).
-constexpr int FW_WARPS = 8, FW_MAXN = 384, FW_PPL = FW_MAXN / 32;
+constexpr int FW_WARPS = 4, FW_MAXN = 512, FW_PPL = FW_MAXN / 32;
 
-__global__ void __launch_bounds__(FW_WARPS * 32) fps_warp_kernel(const float* pts, int64_t task_stride,
+__global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float* pts, int64_t task_stride,
                                                                  const int32_t* count, const int32_t* any,
                                                                  int64_t count_stride, int n_fixed, int n_tasks,
                                                                  int m, float* out_pts, int64_t out_stride,
                                                                  int32_t* out_idx) {
-  __shared__ float s_p[FW_WARPS][3][FW_MAXN];
-  extern __shared__ unsigned short s_sel_all[];  // FW_WARPS * m selected indices (n <= 384 fits 16 bits)
+  // dynamic smem: FW_WARPS x [3][FW_MAXN] f32 point planes, then FW_WARPS x m selected indices (u16)
+  extern __shared__ __align__(16) unsigned char fw_smem[];
+  float* s_p = reinterpret_cast<float*>(fw_smem);
+  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * FW_WARPS * 3 * FW_MAXN);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int task = blockIdx.x * FW_WARPS + warp;
   if (task >= n_tasks) return;
@@ -344,58 +428,21 @@ __global__ void __launch_bounds__(FW_WARPS * 32) fps_warp_kernel(const float* pt
     return;
   }
   if (n > FW_MAXN) return;  // fps_kernel handles it
-  float* sx = s_p[warp][0];
-  float* sy = s_p[warp][1];
-  float* sz = s_p[warp][2];
+  float* sx = s_p + (size_t)warp * 3 * FW_MAXN;
+  float* sy = sx + FW_MAXN;
+  float* sz = sy + FW_MAXN;
   unsigned short* sel = s_sel_all + warp * m;
   const float* src = pts + (size_t)task * task_stride;
   for (int i = lane; i < 3 * n; i += 32) {
     const float v = src[i];
     const int k = i / 3, c = i - 3 * k;
-    s_p[warp][c][k] = v;
+    sx[c * FW_MAXN + k] = v;
   }
   __syncwarp();
-  int lg = 31 - __clz(n);
-  if (lg > 9) lg = 9;
-  const uint32_t bmask = (1u << lg) - 1u;
-  float temp[FW_PPL];
-  uint32_t lokey[FW_PPL];  // 0 = not a candidate
-#pragma unroll
-  for (int i = 0; i < FW_PPL; ++i) {
-    const int k = lane + 32 * i;
-    temp[i] = 1e10f;
-    lokey[i] = 0u;
-    if (k < n) {
-      const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
-      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
-      if (mag > 1e-3f) {
-        const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
-        lokey[i] = ~((rev << 16) | (uint32_t)k);
-      }
-    }
-  }
-  int old = 0;
-  if (lane == 0) sel[0] = 0;
-  for (int j = 1; j < m; ++j) {
-    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-    uint32_t bhi = 0, blo = 0;
-#pragma unroll
-    for (int i = 0; i < FW_PPL; ++i) {
-      const int k = lane + 32 * i;
-      if (lokey[i] != 0u) {
-        const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float d2 = fminf(d, temp[i]);
-        temp[i] = d2;
-        const uint32_t hi = __float_as_uint(d2) + 1u;
-        if (hi > bhi || (hi == bhi && lokey[i] > blo)) { bhi = hi; blo = lokey[i]; }
-      }
-    }
-    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
-    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
-    old = (whi == 0) ? 0 : (int)((~wlo) & 0xffffu);
-    if (lane == 0) sel[j] = (unsigned short)old;
-  }
+  if (n <= 128) fps_warp_picks<4>(sx, sy, sz, n, m, lane, sel);
+  else if (n <= 256) fps_warp_picks<8>(sx, sy, sz, n, m, lane, sel);
+  else if (n <= 384) fps_warp_picks<12>(sx, sy, sz, n, m, lane, sel);
+  else fps_warp_picks<FW_PPL>(sx, sy, sz, n, m, lane, sel);
   __syncwarp();
   for (int i = lane; i < m; i += 32) {
     const int k = sel[i];
@@ -469,11 +516,17 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nmax = count ? task_stride / 3 : n_fixed;
   IGI_REQUIRE(nmax <= 0xffff, "igi_fps: at most 65535 points per task");
-  const bool warp_ok = (size_t)FW_WARPS * m * 2 <= 48 * 1024 - sizeof(float) * FW_WARPS * 3 * FW_MAXN;
+  const size_t warp_smem = sizeof(float) * FW_WARPS * 3 * FW_MAXN + (size_t)FW_WARPS * m * 2;
+  const bool warp_ok = warp_smem <= 28 * 1024;  // keeps 8 CTAs (32 task warps) per SM
   const bool need_block = !warp_ok || nmax > FW_MAXN;
   const bool need_warp = warp_ok && (count != nullptr || n_fixed <= FW_MAXN);
   if (need_warp) {
-    fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, (size_t)FW_WARPS * m * 2, st>>>(
+    static bool warp_attr = false;
+    if (!warp_attr) {
+      IGI_CUDA(cudaFuncSetAttribute(fps_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+      warp_attr = true;
+    }
+    fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, warp_smem, st>>>(
         pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m, out_pts, out_stride, out_idx);
     IGI_CHECK_LAUNCH("fps_warp_kernel");
   }
@@ -486,8 +539,13 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
       IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
-    fps_kernel<<<n_tasks, kFpsBlock, smem, st>>>(pts, task_stride, count, any, count_stride, n_fixed, m, out_pts,
-                                                 out_stride, out_idx, need_warp ? FW_MAXN + 1 : 0);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
+    const int grid = n_tasks < sms * per_sm ? n_tasks : sms * per_sm;
+    fps_kernel<<<grid, kFpsBlock, smem, st>>>(pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m,
+                                              out_pts, out_stride, out_idx, need_warp ? FW_MAXN + 1 : 0);
     IGI_CHECK_LAUNCH("fps_kernel");
   }
   return IGI_OK;

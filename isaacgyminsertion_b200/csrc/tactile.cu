@@ -317,6 +317,9 @@ __device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid
 
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
+#ifndef GEOM_VIS_TEST
+#define GEOM_VIS_TEST 1
+#endif
 constexpr int GEOM_EXACT_AREA = 100;  // boxes up to this many pixels are visibility-tested exactly
 
 __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
@@ -421,7 +424,8 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
       // visibility against the gel: small boxes are scanned exactly (same arithmetic as the
       // raster), large ones block by block with the conservative bound; invisible triangles are
       // dropped here so the contact kernel only sees what can produce a fragment
-      if ((x1 - x0 + 1) * (y1 - y0 + 1) <= GEOM_EXACT_AREA) {
+      if (GEOM_VIS_TEST == 0) {
+      } else if ((x1 - x0 + 1) * (y1 - y0 + 1) <= GEOM_EXACT_AREA) {
         bool vis = false;
         for (int py = y0; py <= y1 && !vis; ++py)
           for (int px = x0; px <= x1; ++px) {
