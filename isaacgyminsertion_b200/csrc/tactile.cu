@@ -538,9 +538,8 @@ struct ContactArgs {
 };
 constexpr int CT_BLOCK = 256;
 constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
-constexpr int CT_BUD_GRAY = 8192;    // region pixels (interior + halo) held in shared memory, 8 B each
+constexpr int CT_BUD_GRAY = 7936;    // region pixels (interior + halo) held in shared memory, 8 B each
 constexpr int CT_BUD_RGB = 4096;     // three-channel path: + 24 B per pixel of difference / blur planes
-constexpr int CT_COOP_SPAN = 24;     // row spans longer than this are rastered by the whole warp
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -595,8 +594,26 @@ __device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, flo
   }
 }
 
+// Optional per-phase cycle counters (build with -DCT_PROFILE; read with igi_debug_read_prof).
+#ifdef CT_PROFILE
+__device__ unsigned long long g_ct_prof[16];
+#define CT_T(slot)                                                     \
+  do {                                                                 \
+    if (threadIdx.x == 0) {                                            \
+      const long long now__ = clock64();                               \
+      atomicAdd(&g_ct_prof[slot], (unsigned long long)(now__ - t_prof)); \
+      t_prof = now__;                                                  \
+    }                                                                  \
+  } while (0)
+#else
+#define CT_T(slot) do { } while (0)
+#endif
+
 template <int NCH>
 __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(ContactArgs a) {
+#ifdef CT_PROFILE
+  long long t_prof = clock64();
+#endif
   constexpr int BUD = NCH == 1 ? CT_BUD_GRAY : CT_BUD_RGB;
   constexpr int DS = NCH == 1 ? 2 : 3;  // float stride between pixels of the difference / blur planes
   extern __shared__ __align__(16) unsigned char ct_smem[];
@@ -610,10 +627,13 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
   __shared__ float sM[12];
   __shared__ int s_hits, s_frame;
   __shared__ int s_hb[4];  // bounds of the pixels that changed (hits dilated by the blur radius)
+  __shared__ unsigned short s_q[CT_BLOCK / 32][64];  // per-warp queue of hit pixels waiting to be shaded
+  __shared__ double s_rb[511];            // remove_bg: d / 255.0 + 0.5 for d = -255..255 (f64 divide once)
   __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CT_BLOCK / 32;
   for (int i = tid; i < TW; i += CT_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
+  for (int i = tid; i < 511; i += CT_BLOCK) s_rb[i] = (double)(i - 255) / 255.0 + 0.5;
   const float span_x0 = k_dxp[0], span_kx = (float)(TW - 1) / (k_dxp[TW - 1] - k_dxp[0]);
   for (;;) {
     __syncthreads();
@@ -624,6 +644,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
     }
     __syncthreads();
     const int f = s_frame;
+    CT_T(0);
     if (f < 0) return;
     if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const int K = a.counts[f];
@@ -651,20 +672,30 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
         const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
         __syncthreads();
-        // --- z-buffer starts as the gel
-        for (int ry = warp; ry < RH; ry += NW) {
-          const int py = ry0 + ry;
-          for (int rx = lane; rx < RW; rx += 32) {
-            const int px = rx0 + rx;
-            unsigned long long key = ZEMPTY;
-            if (px >= cx0 && px <= cx1 && py >= cy0 && py <= cy1) {
-              const float d0 = __ldg(a.depth0 + py * TW + px);
-              if (d0 != 0.0f) key = (unsigned long long)__float_as_uint(d0) << 32;
+        // --- z-buffer starts as the gel (flattened over the region, 4 independent loads in flight)
+        {
+          const int npx = RW * RH;
+          const uint32_t inv_rw = 0xffffffffu / (uint32_t)RW + 1u;  // exact floor(i / RW) for i < 2^16
+          for (int i0 = tid; i0 < npx; i0 += 4 * CT_BLOCK) {
+            float d0[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * CT_BLOCK;
+              const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
+              const int px = rx0 + rx, py = ry0 + ry;
+              in[u] = i < npx && px >= cx0 && px <= cx1 && py >= cy0 && py <= cy1;
+              d0[u] = in[u] ? __ldg(a.depth0 + py * TW + px) : 0.0f;
             }
-            s_z[ry * RW + rx] = key;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u * CT_BLOCK;
+              if (i < npx) s_z[i] = d0[u] != 0.0f ? (unsigned long long)__float_as_uint(d0[u]) << 32 : ZEMPTY;
+            }
           }
         }
         if (tid == 0) s_hits = 0;
+        CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
         for (int c0 = 0; c0 < K; c0 += CT_CHUNK) {
@@ -705,6 +736,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
             base += rows[j];
           }
           __syncthreads();
+          CT_T(2);
           for (int i0 = warp * 32; i0 < total; i0 += CT_BLOCK) {
             const int i = i0 + lane;
             int k = 0, py = 0, xlo = 0, xhi = -1;
@@ -722,89 +754,113 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
               py = by0 + (i - s_off[lo]);
               row_span(s, s_dyp[py], span_x0, span_kx, bx0, bx1, xlo, xhi);
             }
-            // long spans: the whole warp takes them, one pixel per lane
-            unsigned big = __ballot_sync(0xffffffffu, xhi - xlo + 1 > CT_COOP_SPAN);
-            while (big) {
-              const int src = __ffs(big) - 1;
-              big &= big - 1;
-              const int kk = __shfl_sync(0xffffffffu, k, src), yy = __shfl_sync(0xffffffffu, py, src);
-              const int xa = __shfl_sync(0xffffffffu, xlo, src), xb = __shfl_sync(0xffffffffu, xhi, src);
-              const Setup ss = load_setup(list + kk);
-              unsigned long long* zrow = s_z + (yy - ry0) * RW - rx0;
-              const float dyy = s_dyp[yy];
-              for (int px = xa + lane; px <= xb; px += 32) raster_frag(ss, kk, s_dxp[px], dyy, zrow + px, &s_hits);
-              if (lane == src) xhi = -1;
+            // The 32 row spans of the warp are flattened into one pixel list (warp scan of the span
+            // lengths) and dealt out one pixel per lane, so lanes stay busy whatever the span lengths.
+            const int len = max(xhi - xlo + 1, 0);
+            int excl = len;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, excl, d);
+              if (lane >= d) excl += t;
             }
-            if (xlo <= xhi) {
-              unsigned long long* zrow = s_z + (py - ry0) * RW - rx0;
-              const float dy = s_dyp[py];
-              for (int px = xlo; px <= xhi; ++px) raster_frag(s, k, s_dxp[px], dy, zrow + px, &s_hits);
+            const int npix = __shfl_sync(0xffffffffu, excl, 31);
+            excl -= len;
+            for (int p0 = 0; p0 < npix; p0 += 32) {
+              const int p = p0 + lane;
+              int src = 0;  // last lane whose span starts at or before pixel p
+#pragma unroll
+              for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, excl, src + step);   // src + step <= 31
+                if (v <= p) src += step;
+              }
+              const int kk = __shfl_sync(0xffffffffu, k, src), yy = __shfl_sync(0xffffffffu, py, src);
+              const int px = __shfl_sync(0xffffffffu, xlo, src) + (p - __shfl_sync(0xffffffffu, excl, src));
+              if (p < npix) {
+                const Setup ss = load_setup(list + kk);
+                raster_frag(ss, kk, s_dxp[px], s_dyp[yy], s_z + (yy - ry0) * RW + (px - rx0), &s_hits);
+              }
             }
           }
         }
         __syncthreads();
+        CT_T(3);
         if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
-        // --- shade hits, build the scaled difference image (0 where the gel is visible)
-        for (int ry = warp; ry < RH; ry += NW) {
-          const int py = ry0 + ry;
-          bool rowhit = false;
-          int hx0 = TW, hx1 = -1;
-          for (int rx = lane; rx < RW; rx += 32) {
-            const int px = rx0 + rx;
-            const int i = ry * RW + rx;
+        // --- shade hits, build the scaled difference image (0 where the gel is visible).  Each warp
+        // scans 32 region pixels at a time, queues the hit ones and shades a full warp of them
+        // whenever 32 are waiting, so the long shading path runs with all lanes active.
+        {
+          const int npx = RW * RH;
+          const uint32_t inv_rw = 0xffffffffu / (uint32_t)RW + 1u;
+          unsigned short* q = s_q[warp];
+          int qn = 0;
+          int hx0 = TW, hx1 = -1, hy0 = TH, hy1 = -1;
+          auto shade_px = [&](int i) {
+            const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
+            const int px = rx0 + rx, py = ry0 + ry;
             const unsigned long long key = s_z[i];
             const uint32_t low = (uint32_t)key;
-            float d[NCH];
+            const float t = __uint_as_float((uint32_t)(key >> 32));
+            const Setup s = load_setup(list + (int)((low - 1u) & 0xfffu));
+            const float dx = s_dxp[px], dy = s_dyp[py];
+            const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
+            const float es = add(add(e0, e1), e2);
+            const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
+            const float l0 = sub(sub(1.0f, l1), l2);
+            const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
+            float no[3];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) d[c] = 0.f;
-            const bool hit = key != ZEMPTY && low != 0u;
-            if (hit) {
-              const float t = __uint_as_float((uint32_t)(key >> 32));
-              const Setup s = load_setup(list + (int)((low - 1u) & 0xfffu));
-              const float dx = s_dxp[px], dy = s_dyp[py];
-              const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
-              const float es = add(add(e0, e1), e2);
-              const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
-              const float l0 = sub(sub(1.0f, l1), l2);
-              const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
-              float no[3];
+            for (int c = 0; c < 3; ++c)
+              no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
+            V3 n;
+            n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
+            n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
+            n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
+            n = normalize(n);
+            V3 pp{mul(dx, t), mul(dy, t), -t};
+            uint8_t rgb[3];
+            shade_t<NCH>(pp, n, rgb);
+            const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
+            // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
+            if (px >= tx && px <= ix1 && py >= ty && py <= iy1)
+              gdep[py * TW + px] = sub(__ldg(a.depth0 + py * TW + px), t);
 #pragma unroll
-              for (int c = 0; c < 3; ++c)
-                no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
-              V3 n;
-              n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
-              n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
-              n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
-              n = normalize(n);
-              V3 p{mul(dx, t), mul(dy, t), -t};
-              uint8_t rgb[3];
-              shade_t<NCH>(p, n, rgb);
-              const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
+            for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
+            hx0 = min(hx0, px); hx1 = max(hx1, px); hy0 = min(hy0, py); hy1 = max(hy1, py);
+          };
+          for (int base = warp * 32; base < npx; base += CT_BLOCK) {
+            const int i = base + lane;
+            bool hit = false;
+            if (i < npx) {
+              const unsigned long long key = s_z[i];
+              hit = key != ZEMPTY && (uint32_t)key != 0u;
+              if (!hit) {
 #pragma unroll
-              for (int c = 0; c < NCH; ++c) d[c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
-              // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
-              if (px >= tx && px <= ix1 && py >= ty && py <= iy1)
-                gdep[py * TW + px] = sub(__ldg(a.depth0 + py * TW + px), t);
-              rowhit = true;
-              hx0 = min(hx0, px); hx1 = max(hx1, px);
+                for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = 0.f;
+              }
             }
-            if (NCH == 1) {
-              s_diff[DS * i] = d[0];
-            } else {
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = d[c];
+            const unsigned bm = __ballot_sync(0xffffffffu, hit);
+            if (hit) q[qn + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i;
+            qn += __popc(bm);
+            __syncwarp();
+            if (qn >= 32) {
+              qn -= 32;
+              const int idx = q[qn + lane];
+              __syncwarp();
+              shade_px(idx);
             }
           }
-          if (__any_sync(0xffffffffu, rowhit)) {
-            hx0 = __reduce_min_sync(0xffffffffu, hx0);
-            hx1 = __reduce_max_sync(0xffffffffu, hx1);
+          if (lane < qn) shade_px(q[lane]);
+          if (__any_sync(0xffffffffu, hx1 >= 0)) {
+            hx0 = __reduce_min_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1);
+            hy0 = __reduce_min_sync(0xffffffffu, hy0); hy1 = __reduce_max_sync(0xffffffffu, hy1);
             if (lane == 0) {
               atomicMin(&s_hb[0], hx0); atomicMax(&s_hb[2], hx1);
-              atomicMin(&s_hb[1], py); atomicMax(&s_hb[3], py);
+              atomicMin(&s_hb[1], hy0); atomicMax(&s_hb[3], hy1);
             }
           }
         }
         __syncthreads();
+        CT_T(4);
         // --- 7-tap horizontal pass over the interior columns (BORDER_REFLECT_101 at the image edge)
         const int iw = ix1 - tx + 1;
         for (int ry = warp; ry < RH; ry += NW) {
@@ -829,7 +885,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
           }
         }
         __syncthreads();
-        // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8))
+        CT_T(5);
+        // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8)).  The per-channel change
+        // (colour - bg_real, 10 bits each) is left in the pixel's dead low word for the obs stage.
         for (int ly = warp; ly <= iy1 - ty; ly += NW) {
           const int py = ty + ly;
           for (int lx = lane; lx < iw; lx += 32) {
@@ -846,15 +904,22 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
               for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, hp[c], acc[c]);
             }
             const size_t o = ((size_t)py * TW + px) * 3;
+            uint32_t packed = 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)bgr[o + c], kc.clip_lo, kc.clip_hi);
-              col[o + c] = (uint8_t)v;
+              const int b = (int)__ldg(bgr + o + c);
+              const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)b, kc.clip_lo, kc.clip_hi);
+              const int q = (int)(uint8_t)v;
+              col[o + c] = (uint8_t)q;
+              packed |= (uint32_t)(q - b + 256) << (10 * c);
             }
+            if (NCH == 1) reinterpret_cast<uint32_t*>(s_z)[2 * ((py - ry0) * RW + (px - rx0))] = packed;
           }
         }
+        CT_T(6);
       }
     __syncthreads();
+    CT_T(7);
     // --- obs pixels whose 3.5x3.5 source window meets a pixel that changed ---------------------
     // flipud + crop: obs row r reads flipped rows [3.5r, 3.5r+3.5) = original rows 223 - that.
     if (s_hb[2] >= 0) {
@@ -866,6 +931,11 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
       const int nw = ox1 - ox0 + 1, nh = oy1 - oy0 + 1;
       float* ob = a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
                   (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride;
+      // One region held the whole window: every changed pixel's (colour - bg_real) sits in shared
+      // memory and everything outside the window is unchanged (difference 0), so no global reads.
+      const bool from_smem = NCH == 1 && nsx == 1 && nsy == 1;
+      const uint32_t* s_delta = reinterpret_cast<const uint32_t*>(s_z);
+      const int rx0 = wx0 - HALO, ry0 = wy0 - HALO;
       for (int i = tid; i < nw * nh; i += CT_BLOCK) {
         const int oy = oy0 + i / nw, ox = ox0 + i % nw;
         // cv2 INTER_AREA, scale 3.5: taps for even/odd destination index
@@ -881,10 +951,20 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
             const int px = sx0 + k;
             const int ddx = px - TW / 2, ddy = py - TH / 2;
             const double m = (ddx * ddx + ddy * ddy <= (TW / 2) * (TW / 2)) ? 1.0 : 0.0;  // circle_mask
-            const size_t o = ((size_t)py * TW + px) * 3;
+            int dl[3];
+            if (from_smem) {
+              uint32_t pk = (256u << 20) | (256u << 10) | 256u;
+              if (px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1) pk = s_delta[2 * ((py - ry0) * RW + (px - rx0))];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) dl[c] = (int)((pk >> (10 * c)) & 1023u) - 256;
+            } else {
+              const size_t o = ((size_t)py * TW + px) * 3;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) dl[c] = (int)col[o + c] - (int)bgr[o + c];
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const double v = ((double)((int)col[o + c] - (int)bgr[o + c]) / 255.0 + 0.5) * m;  // remove_bg * mask
+              const double v = s_rb[dl[c] + 255] * m;  // remove_bg * mask
               racc[c] += v * (double)wx;
             }
           }
@@ -896,6 +976,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
         ob[oy * OBS_W + ox] = g;
       }
     }
+    CT_T(8);
   }
 }
 
@@ -1090,6 +1171,18 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   }
   return IGI_OK;
 }
+
+#ifdef CT_PROFILE
+extern "C" int igi_debug_read_prof(unsigned long long* out16, int reset) {
+  IGI_CUDA(cudaDeviceSynchronize());
+  IGI_CUDA(cudaMemcpyFromSymbol(out16, g_ct_prof, sizeof(unsigned long long) * 16));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    IGI_CUDA(cudaMemcpyToSymbol(g_ct_prof, z, sizeof(z)));
+  }
+  return IGI_OK;
+}
+#endif
 
 extern "C" int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames,
                                float* obs, int64_t obs_stride, void* stream) {
