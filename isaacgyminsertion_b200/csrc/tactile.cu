@@ -128,6 +128,27 @@ __device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
   return x0 <= x1 && y0 <= y1;
 }
 
+// Same box with reciprocal multiplies (geometry kernel: the +-1 pixel dilation absorbs the ulps).
+__device__ __forceinline__ bool tri_bbox_fast(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
+  const float zn = kc.znear;
+  const float zA = -A.z, zB = -B.z, zC = -C.z;
+  if (fminf(zA, fminf(zB, zC)) < zn) return tri_bbox(A, B, C, x0, y0, x1, y1);  // near-plane cases: general path
+  const float ra = __fdividef(1.0f, zA), rb = __fdividef(1.0f, zB), rc = __fdividef(1.0f, zC);
+  const float ax = A.x * ra, ay = A.y * ra, bx = B.x * rb, by = B.y * rb, cx = C.x * rc, cy = C.y * rc;
+  const float mnx = fminf(ax, fminf(bx, cx)), mxx = fmaxf(ax, fmaxf(bx, cx));
+  const float mny = fminf(ay, fminf(by, cy)), mxy = fmaxf(ay, fmaxf(by, cy));
+  const float sx0 = k_dxp[0], sx1 = k_dxp[TW - 1], sy0 = k_dyp[0], sy1 = k_dyp[TH - 1];
+  const float kx = __fdividef((float)(TW - 1), sx1 - sx0), ky = __fdividef((float)(TH - 1), sy1 - sy0);
+  const float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
+  const float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
+  if (fx1 < -2.0f || fy1 < -2.0f || fx0 > (float)(TW + 1) || fy0 > (float)(TH + 1)) return false;
+  x0 = (int)fmaxf(floorf(fx0) - 1.0f, 0.0f);
+  y0 = (int)fmaxf(floorf(fy0) - 1.0f, 0.0f);
+  x1 = (int)fminf(ceilf(fx1) + 1.0f, (float)(TW - 1));
+  y1 = (int)fminf(ceilf(fy1) + 1.0f, (float)(TH - 1));
+  return x0 <= x1 && y0 <= y1;
+}
+
 // coverage + depth of one pixel; returns t (depth) or -1 when not covered / clipped
 __device__ __forceinline__ float cover(const Setup& s, float dx, float dy, float& e1, float& e2, float& esum) {
   const float e0 = edge_fn(dx, dy, s.n0);
@@ -150,8 +171,9 @@ __device__ __forceinline__ float cover(const Setup& s, float dx, float dy, float
 // functions and the depth denominator are affine in the ray slopes, so their extreme over the
 // block sits at a corner; a relative margin keeps the bound conservative against the
 // separately-rounded per-pixel arithmetic of cover().
-__device__ __forceinline__ bool block_may_hit(const Setup& s, int x0, int x1, int y0, int y1, float hzmax) {
-  const float dxa = k_dxp[x0], dxb = k_dxp[x1], dya = k_dyp[y0], dyb = k_dyp[y1];
+__device__ __forceinline__ bool block_may_hit(const Setup& s, const float* __restrict__ tdx, const float* __restrict__ tdy,
+                                              int x0, int x1, int y0, int y1, float hzmax) {
+  const float dxa = tdx[x0], dxb = tdx[x1], dya = tdy[y0], dyb = tdy[y1];
   auto lo_bound = [&](V3 n) {  // lower bound of dx*n.x + dy*n.y - n.z over the block
     const float ax = fminf(dxa * n.x, dxb * n.x), ay = fminf(dya * n.y, dyb * n.y);
     const float m = 1e-5f * (fmaxf(fabsf(dxa * n.x), fabsf(dxb * n.x)) +
@@ -178,36 +200,37 @@ __device__ __forceinline__ V3 normalize(V3 v) {
 // the oracle within 1/255.
 template <int NCH>
 __device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
-  const float INV_PI = 0.31830988618379067f;
+  const float A2_PI = kc.sh_a2 * 0.31830988618379067f;
   const float ipl = rsqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
   const V3 v{-p.x * ipl, -p.y * ipl, -p.z * ipl};
   const float a2 = kc.sh_a2;
-  const float nv = clampf(n.x * v.x + n.y * v.y + n.z * v.z, 0.001f, 1.0f);
-  const float av = __fdividef(2.0f * nv, nv + sqrtf(a2 + (1.0f - a2) * (nv * nv)));
+  const float nv_raw = n.x * v.x + n.y * v.y + n.z * v.z;
+  const float nv = clampf(nv_raw, 0.001f, 1.0f);
+  const float gv = nv + sqrtf(a2 + (1.0f - a2) * (nv * nv));   // 2 nv / gv = Smith term of the view direction
   float col[NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) col[k] = 0.f;
   for (int i = 0; i < kc.n_lights; ++i) {
     const V3 L{kc.light_pos[i][0] - p.x, kc.light_pos[i][1] - p.y, kc.light_pos[i][2] - p.z};
-    const float d2 = L.x * L.x + L.y * L.y + L.z * L.z;
-    const float il = rsqrtf(d2);
+    const float il = rsqrtf(L.x * L.x + L.y * L.y + L.z * L.z);
     const V3 l{L.x * il, L.y * il, L.z * il};
-    V3 h{l.x + v.x, l.y + v.y, l.z + v.z};
-    const float ih = rsqrtf(h.x * h.x + h.y * h.y + h.z * h.z);
-    h.x *= ih; h.y *= ih; h.z *= ih;
-    const float nl = clampf(n.x * l.x + n.y * l.y + n.z * l.z, 0.001f, 1.0f);
-    const float nh = clampf(n.x * h.x + n.y * h.y + n.z * h.z, 0.001f, 1.0f);
-    const float vh = clampf(v.x * h.x + v.y * h.y + v.z * h.z, 0.001f, 1.0f);
+    // half vector h = (l + v)/|l + v| with |l + v|^2 = 2 + 2 v.l, so n.h and v.h need no vector h
+    const float vl = v.x * l.x + v.y * l.y + v.z * l.z;
+    const float ih = rsqrtf(fmaxf(2.0f + 2.0f * vl, 1e-20f));
+    const float nl_raw = n.x * l.x + n.y * l.y + n.z * l.z;
+    const float nl = clampf(nl_raw, 0.001f, 1.0f);
+    const float nh = clampf((nl_raw + nv_raw) * ih, 0.001f, 1.0f);
+    const float vh = clampf((vl + 1.0f) * ih, 0.001f, 1.0f);
     const float cd = -(kc.light_dir[i][0] * l.x + kc.light_dir[i][1] * l.y + kc.light_dir[i][2] * l.z);
     float att = clampf(cd * kc.light_las[i] + kc.light_lao[i], 0.0f, 1.0f);
     att = att * att;
     if (kc.inverse_square) att = att * il * il;
     const float w = 1.0f - vh;
     const float w2 = w * w, fw = w2 * w2 * w;
-    const float al = __fdividef(2.0f * nl, nl + sqrtf(a2 + (1.0f - a2) * (nl * nl)));
+    // specular = G_l G_v D / (4 nl nv) with G_x = 2 x / g_x  ->  D / (g_l g_v)
+    const float gl = nl + sqrtf(a2 + (1.0f - a2) * (nl * nl));
     const float f = (nh * a2 - nh) * nh + 1.0f;
-    const float D = __fdividef(a2 * INV_PI, f * f);
-    const float sp = __fdividef(al * av * D, 4.0f * nl * nv);
+    const float sp = __fdividef(A2_PI, f * f * gl * gv);
     const float na = nl * att;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -308,32 +331,71 @@ __device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid
   const float cx = clampf(gx, lo0, hi0), cy = clampf(gy, lo1, hi1), cz = clampf(gz, lo2, hi2);
   const float ddx = gx - cx, ddy = gy - cy, ddz = gz - cz;
   const float dbox = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
-  int ix = min(max((int)((cx - lo0) / h), 0), kc.grid_n[0] - 1);
-  int iy = min(max((int)((cy - lo1) / h), 0), kc.grid_n[1] - 1);
-  int iz = min(max((int)((cz - lo2) / h), 0), kc.grid_n[2] - 1);
+  // cell index by reciprocal multiply: a point within an ulp of a cell face may land in the
+  // neighbouring cell, which the slack (> one cell diagonal) already covers
+  const float ih = __fdividef(1.0f, h);
+  int ix = min(max((int)((cx - lo0) * ih), 0), kc.grid_n[0] - 1);
+  int iy = min(max((int)((cy - lo1) * ih), 0), kc.grid_n[1] - 1);
+  int iz = min(max((int)((cz - lo2) * ih), 0), kc.grid_n[2] - 1);
   const float d = grid[((size_t)iz * kc.grid_n[1] + iy) * kc.grid_n[0] + ix];
   return fmaxf(dbox, d - kc.grid_slack - dbox);
 }
 
+// Optional per-phase cycle counters (build with -DCT_PROFILE; read with igi_debug_read_prof).
+#ifdef CT_PROFILE
+__device__ unsigned long long g_ct_prof[32];
+#define CT_T(slot)                                                     \
+  do {                                                                 \
+    if (threadIdx.x == 0) {                                            \
+      const long long now__ = clock64();                               \
+      atomicAdd(&g_ct_prof[slot], (unsigned long long)(now__ - t_prof)); \
+      t_prof = now__;                                                  \
+    }                                                                  \
+  } while (0)
+#define CT_COUNT(slot, v) do { if ((v) != 0) atomicAdd(&g_ct_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define CT_T(slot) do { } while (0)
+#define CT_COUNT(slot, v) do { } while (0)
+#endif
+
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
-#ifndef GEOM_VIS_TEST
-#define GEOM_VIS_TEST 1
-#endif
-constexpr int GEOM_EXACT_AREA = 100;  // boxes up to this many pixels are visibility-tested exactly
+constexpr int GEOM_SMALL_BLOCKS = 8;   // triangles touching up to this many 8x8 blocks are tested by their own thread
+constexpr int GEOM_MAX_BIG = 160;      // larger ones are queued (with their setup record) and tested by a whole warp
+
+// Shrinks [x0,x1]x[y0,y1] to the 8x8 image blocks of it in which the triangle may produce a fragment in
+// front of the gel (conservative: edge planes and nearest plane depth against level 3 of the depth0
+// max-pyramid).  `lane`/`nl` split the blocks between cooperating lanes.  Returns false if none.
+__device__ __forceinline__ void blocks_visible(const Setup& s, const float* __restrict__ tdx, const float* __restrict__ tdy,
+                                               const float* __restrict__ hz3, int hw3, int x0, int y0, int x1, int y1,
+                                               int lane, int nl, int& vx0, int& vy0, int& vx1, int& vy1) {
+  const int gbx0 = x0 >> 3, gby0 = y0 >> 3;
+  const int nbx = (x1 >> 3) - gbx0 + 1, nb = nbx * ((y1 >> 3) - gby0 + 1);
+  vx0 = TW; vy0 = TH; vx1 = -1; vy1 = -1;
+  for (int b = lane; b < nb; b += nl) {
+    const int gy = gby0 + b / nbx, gx = gbx0 + b - (b / nbx) * nbx;
+    const int cx0 = max(gx * 8, x0), cx1 = min(gx * 8 + 7, x1), cy0 = max(gy * 8, y0), cy1 = min(gy * 8 + 7, y1);
+    if (block_may_hit(s, tdx, tdy, cx0, cx1, cy0, cy1, hz3[gy * hw3 + gx])) {
+      vx0 = min(vx0, cx0); vy0 = min(vy0, cy0); vx1 = max(vx1, cx1); vy1 = max(vy1, cy1);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
   __shared__ float sM[12];
   __shared__ int s_cl[GEOM_MAX_CL];
-  __shared__ int s_ncl, s_count;
+  __shared__ Setup s_big[GEOM_MAX_BIG];
+  __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
+  __shared__ int s_ncl, s_count, s_nbig;
   __shared__ int s_bb[4];
   const int f = blockIdx.x;
   const int env = f / a.sensors_per_env;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (a.update && !a.update[env]) {
     if (tid == 0) a.counts[f] = -1;  // frame not rendered this step
     return;
   }
+  for (int i = tid; i < TW; i += GEOM_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
   if (tid == 0) {
     // ---- pose chain in f64 (xyzquat_to_tf_numpy, update_camera_pose_from_matrix, adjust_with_force)
     double q[4], R[9], Ro[9];
@@ -375,6 +437,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     }
     s_ncl = 0;
     s_count = 0;
+    s_nbig = 0;
     s_bb[0] = TW; s_bb[1] = TH; s_bb[2] = -1; s_bb[3] = -1;
   }
   __syncthreads();
@@ -391,72 +454,94 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
   }
   __syncthreads();
   const int ncl = min(s_ncl, GEOM_MAX_CL);
+  if (tid == 0) { CT_COUNT(16, ncl); CT_COUNT(17, mi.n_cl); }
   Setup* out = a.setups + (size_t)f * a.kmax;
-  // ---- triangles of surviving clusters: transform, back-face cull, interior test, setup
-  for (int c = 0; c < ncl; ++c) {
-    const Cluster cl = a.clusters[s_cl[c]];
-    for (int k = tid; k < cl.count; k += GEOM_BLOCK) {
-      const int face = cl.first + k;
-      const int i0 = a.faces[3 * face], i1 = a.faces[3 * face + 1], i2 = a.faces[3 * face + 2];
-      V3 A = xform(sM, V3{a.verts[3 * i0], a.verts[3 * i0 + 1], a.verts[3 * i0 + 2]});
-      V3 B = xform(sM, V3{a.verts[3 * i1], a.verts[3 * i1 + 1], a.verts[3 * i1 + 2]});
-      V3 C = xform(sM, V3{a.verts[3 * i2], a.verts[3 * i2 + 1], a.verts[3 * i2 + 2]});
+  const float* hz3 = a.hiz + kc.hiz_off[3];
+  const int hw3 = kc.hiz_w[3];
+  auto emit = [&](Setup& s, int face, int x0, int y0, int x1, int y1) {
+    s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+    s.tri = (uint32_t)face;
+    s.orig = (uint32_t)a.face_orig[face];
+    const int slot = atomicAdd(&s_count, 1);
+    if (slot < a.kmax) out[slot] = s;
+    atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1);
+  };
+  // transform + setup + the cheap culls of one face; false = culled
+  auto prepare = [&](int face, Setup& s, int& x0, int& y0, int& x1, int& y1) {
+    const int i0 = a.faces[3 * face], i1 = a.faces[3 * face + 1], i2 = a.faces[3 * face + 2];
+    V3 A = xform(sM, V3{a.verts[3 * i0], a.verts[3 * i0 + 1], a.verts[3 * i0 + 2]});
+    V3 B = xform(sM, V3{a.verts[3 * i1], a.verts[3 * i1 + 1], a.verts[3 * i1 + 2]});
+    V3 C = xform(sM, V3{a.verts[3 * i2], a.verts[3 * i2 + 1], a.verts[3 * i2 + 2]});
+    // face normal + facing first; the three edge planes only for triangles that survive the culls
+    V3 E1{sub(B.x, A.x), sub(B.y, A.y), sub(B.z, A.z)};
+    V3 E2{sub(C.x, A.x), sub(C.y, A.y), sub(C.z, A.z)};
+    s.N = cross3s(E1, E2);
+    s.det = dot3s(s.N, A);
+    CT_COUNT(18, 1);
+    if (!(s.det < 0.0f)) return false;
+    CT_COUNT(19, 1);
+    // bounding sphere of the triangle around its centroid against the gel interior
+    const float gx = (A.x + B.x + C.x) * (1.0f / 3.0f), gy = (A.y + B.y + C.y) * (1.0f / 3.0f),
+                gz = (A.z + B.z + C.z) * (1.0f / 3.0f);
+    auto d2 = [&](V3 P) { return (P.x - gx) * (P.x - gx) + (P.y - gy) * (P.y - gy) + (P.z - gz) * (P.z - gz); };
+    const float rr = sqrtf(fmaxf(d2(A), fmaxf(d2(B), d2(C)))) * 1.0001f + 1e-7f;
+    if (grid_lower_bound(a.grid, gx, gy, gz) > rr) return false;
+    CT_COUNT(20, 1);
+    if (!tri_bbox_fast(A, B, C, x0, y0, x1, y1)) return false;
+    CT_COUNT(21, 1);
+    // hierarchical-Z: nearest possible fragment vs the farthest gel depth under the box
+    int L = 0;
+    while (L < kc.hiz_levels - 1 && (((x1 >> L) - (x0 >> L)) > 1 || ((y1 >> L) - (y0 >> L)) > 1)) ++L;
+    const float* hz = a.hiz + kc.hiz_off[L];
+    const int hw = kc.hiz_w[L];
+    const int ax = x0 >> L, bx = x1 >> L, ay = y0 >> L, by = y1 >> L;
+    const float m = fmaxf(fmaxf(hz[ay * hw + ax], hz[ay * hw + bx]), fmaxf(hz[by * hw + ax], hz[by * hw + bx]));
+    const float zmin = fmaxf(fminf(-A.z, fminf(-B.z, -C.z)), kc.znear);
+    if (zmin > m) return false;
+    CT_COUNT(22, 1);
+    s.n0 = cross3s(B, C);
+    s.n1 = cross3s(C, A);
+    s.n2 = cross3s(A, B);
+    return true;
+  };
+
+  // ---- faces of the surviving clusters, flattened so that every thread has one (clusters hold <= 64)
+  for (int it = tid; it < ncl * 64; it += GEOM_BLOCK) {
+    const int2 cl = *reinterpret_cast<const int2*>(&a.clusters[s_cl[it >> 6]].first);  // first, count
+    for (int k = it & 63; k < cl.y; k += 64) {  // clusters normally hold <= 64 faces: one pass
+      const int face = cl.x + k;
       Setup s;
-      if (!make_setup(A, B, C, s)) continue;
-      // bounding sphere of the triangle around its centroid
-      const float gx = (A.x + B.x + C.x) * (1.0f / 3.0f), gy = (A.y + B.y + C.y) * (1.0f / 3.0f),
-                  gz = (A.z + B.z + C.z) * (1.0f / 3.0f);
-      auto d2 = [&](V3 P) { return (P.x - gx) * (P.x - gx) + (P.y - gy) * (P.y - gy) + (P.z - gz) * (P.z - gz); };
-      const float rr = sqrtf(fmaxf(d2(A), fmaxf(d2(B), d2(C)))) * 1.0001f + 1e-7f;
-      if (grid_lower_bound(a.grid, gx, gy, gz) > rr) continue;
       int x0, y0, x1, y1;
-      if (!tri_bbox(A, B, C, x0, y0, x1, y1)) continue;
-      {  // hierarchical-Z: nearest possible fragment vs the farthest gel depth under the box
-        int L = 0;
-        while (L < kc.hiz_levels - 1 && (((x1 >> L) - (x0 >> L)) > 1 || ((y1 >> L) - (y0 >> L)) > 1)) ++L;
-        const float* hz = a.hiz + kc.hiz_off[L];
-        const int hw = kc.hiz_w[L];
-        const int ax = x0 >> L, bx = x1 >> L, ay = y0 >> L, by = y1 >> L;
-        const float m = fmaxf(fmaxf(hz[ay * hw + ax], hz[ay * hw + bx]), fmaxf(hz[by * hw + ax], hz[by * hw + bx]));
-        const float zmin = fmaxf(fminf(-A.z, fminf(-B.z, -C.z)), kc.znear);
-        if (zmin > m) continue;
+      if (!prepare(face, s, x0, y0, x1, y1)) continue;
+      // visibility against the gel, block by block; triangles over many blocks go to the warp queue
+      const int nb = ((x1 >> 3) - (x0 >> 3) + 1) * ((y1 >> 3) - (y0 >> 3) + 1);
+      if (nb > GEOM_SMALL_BLOCKS) {
+        const int slot = atomicAdd(&s_nbig, 1);
+        if (slot < GEOM_MAX_BIG) {
+          s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+          s.tri = (uint32_t)face;
+          s_big[slot] = s;
+          continue;
+        }
       }
-      // visibility against the gel: small boxes are scanned exactly (same arithmetic as the
-      // raster), large ones block by block with the conservative bound; invisible triangles are
-      // dropped here so the contact kernel only sees what can produce a fragment
-      if (GEOM_VIS_TEST == 0) {
-      } else if ((x1 - x0 + 1) * (y1 - y0 + 1) <= GEOM_EXACT_AREA) {
-        bool vis = false;
-        for (int py = y0; py <= y1 && !vis; ++py)
-          for (int px = x0; px <= x1; ++px) {
-            float e1, e2, es;
-            const float t = cover(s, k_dxp[px], k_dyp[py], e1, e2, es);
-            if (t < 0.0f) continue;
-            const float d0 = __ldg(a.depth0 + py * TW + px);
-            if (d0 == 0.0f || t < d0) { vis = true; break; }
-          }
-        if (!vis) continue;
-      } else {
-        const float* hz3 = a.hiz + kc.hiz_off[3];
-        const int hw3 = kc.hiz_w[3];
-        int vx0 = TW, vy0 = TH, vx1 = -1, vy1 = -1;
-        for (int gy = y0 >> 3; gy <= (y1 >> 3); ++gy)
-          for (int gx = x0 >> 3; gx <= (x1 >> 3); ++gx) {
-            const int cx0 = max(gx * 8, x0), cx1 = min(gx * 8 + 7, x1), cy0 = max(gy * 8, y0), cy1 = min(gy * 8 + 7, y1);
-            if (block_may_hit(s, cx0, cx1, cy0, cy1, hz3[gy * hw3 + gx])) {
-              vx0 = min(vx0, cx0); vy0 = min(vy0, cy0); vx1 = max(vx1, cx1); vy1 = max(vy1, cy1);
-            }
-          }
-        if (vx1 < 0) continue;
-        x0 = vx0; y0 = vy0; x1 = vx1; y1 = vy1;  // shrink the box to the blocks that may hit
-      }
-      s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
-      s.tri = (uint32_t)face;
-      s.orig = (uint32_t)a.face_orig[face];
-      const int slot = atomicAdd(&s_count, 1);
-      if (slot < a.kmax) out[slot] = s;
-      atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1);
+      int vx0, vy0, vx1, vy1;
+      blocks_visible(s, s_dxp, s_dyp, hz3, hw3, x0, y0, x1, y1, 0, 1, vx0, vy0, vx1, vy1);
+      if (vx1 < 0) continue;
+      emit(s, face, vx0, vy0, vx1, vy1);
     }
+  }
+  __syncthreads();
+  // ---- queued large triangles: one warp each, lanes over the 8x8 blocks
+  const int nbig = min(s_nbig, GEOM_MAX_BIG);
+  for (int q = warp; q < nbig; q += GEOM_BLOCK / 32) {
+    Setup s = s_big[q];
+    const int face = (int)s.tri;
+    const int x0 = (int)(s.bbox & 255u), y0 = (int)((s.bbox >> 8) & 255u), x1 = (int)((s.bbox >> 16) & 255u), y1 = (int)(s.bbox >> 24);
+    int vx0, vy0, vx1, vy1;
+    blocks_visible(s, s_dxp, s_dyp, hz3, hw3, x0, y0, x1, y1, lane, 32, vx0, vy0, vx1, vy1);
+    vx0 = __reduce_min_sync(0xffffffffu, vx0); vy0 = __reduce_min_sync(0xffffffffu, vy0);
+    vx1 = __reduce_max_sync(0xffffffffu, vx1); vy1 = __reduce_max_sync(0xffffffffu, vy1);
+    if (lane == 0 && vx1 >= 0) emit(s, face, vx0, vy0, vx1, vy1);
   }
   __syncthreads();
   if (tid == 0) {
@@ -594,21 +679,6 @@ __device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, flo
   }
 }
 
-// Optional per-phase cycle counters (build with -DCT_PROFILE; read with igi_debug_read_prof).
-#ifdef CT_PROFILE
-__device__ unsigned long long g_ct_prof[16];
-#define CT_T(slot)                                                     \
-  do {                                                                 \
-    if (threadIdx.x == 0) {                                            \
-      const long long now__ = clock64();                               \
-      atomicAdd(&g_ct_prof[slot], (unsigned long long)(now__ - t_prof)); \
-      t_prof = now__;                                                  \
-    }                                                                  \
-  } while (0)
-#else
-#define CT_T(slot) do { } while (0)
-#endif
-
 template <int NCH>
 __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(ContactArgs a) {
 #ifdef CT_PROFILE
@@ -737,9 +807,10 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
           }
           __syncthreads();
           CT_T(2);
+          if (tid == 0) { CT_COUNT(9, total); CT_COUNT(12, 1); CT_COUNT(13, RW * RH); CT_COUNT(14, kn); }
           for (int i0 = warp * 32; i0 < total; i0 += CT_BLOCK) {
             const int i = i0 + lane;
-            int k = 0, py = 0, xlo = 0, xhi = -1;
+            int k = 0, py = 0, xlo = 0, xhi = -1, exact = 1;
             Setup s;
             if (i < total) {
               int lo = 0, hi = kn - 1;
@@ -752,7 +823,24 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
               const int bx0 = max((int)(s.bbox & 255u), cx0), by0 = max((int)((s.bbox >> 8) & 255u), cy0);
               const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1);
               py = by0 + (i - s_off[lo]);
-              row_span(s, s_dyp[py], span_x0, span_kx, bx0, bx1, xlo, xhi);
+              const float dy = s_dyp[py];
+              row_span(s, dy, span_x0, span_kx, bx0, bx1, xlo, xhi);
+              // Each edge value is a monotone function of the column even with its roundings (products
+              // and sums round monotonically), so the covered columns of a row form ONE interval.
+              // Walk the conservative ends inwards to the exact ends (normally 0-1 steps): the
+              // pixels in between then need no edge test at all, only depth.
+              auto inside = [&](int px) {
+                const float dx = s_dxp[px];
+                return edge_in(edge_fn(dx, dy, s.n0), s.n0) && edge_in(edge_fn(dx, dy, s.n1), s.n1) &&
+                       edge_in(edge_fn(dx, dy, s.n2), s.n2);
+              };
+              int tries = 0;
+              while (xlo <= xhi && tries < 3 && !inside(xlo)) { ++xlo; ++tries; }
+              bool ok = xlo > xhi || tries < 3 || inside(xlo);
+              tries = 0;
+              while (xlo < xhi && tries < 3 && !inside(xhi)) { --xhi; ++tries; }
+              ok = ok && (xlo >= xhi || tries < 3 || inside(xhi));
+              exact = ok ? 1 : 0;
             }
             // The 32 row spans of the warp are flattened into one pixel list (warp scan of the span
             // lengths) and dealt out one pixel per lane, so lanes stay busy whatever the span lengths.
@@ -765,6 +853,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
             }
             const int npix = __shfl_sync(0xffffffffu, excl, 31);
             excl -= len;
+            if (lane == 0) CT_COUNT(10, npix);
             for (int p0 = 0; p0 < npix; p0 += 32) {
               const int p = p0 + lane;
               int src = 0;  // last lane whose span starts at or before pixel p
@@ -773,11 +862,30 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
                 const int v = __shfl_sync(0xffffffffu, excl, src + step);   // src + step <= 31
                 if (v <= p) src += step;
               }
-              const int kk = __shfl_sync(0xffffffffu, k, src), yy = __shfl_sync(0xffffffffu, py, src);
-              const int px = __shfl_sync(0xffffffffu, xlo, src) + (p - __shfl_sync(0xffffffffu, excl, src));
+              const int kk = __shfl_sync(0xffffffffu, k, src);
+              const int yx = __shfl_sync(0xffffffffu, py | (exact << 8) | (xlo << 16), src);
+              const int yy = yx & 255, px = (yx >> 16) + (p - __shfl_sync(0xffffffffu, excl, src));
               if (p < npix) {
-                const Setup ss = load_setup(list + kk);
-                raster_frag(ss, kk, s_dxp[px], s_dyp[yy], s_z + (yy - ry0) * RW + (px - rx0), &s_hits);
+                unsigned long long* zp = s_z + (yy - ry0) * RW + (px - rx0);
+                const float dx = s_dxp[px], dy = s_dyp[yy];
+                if (yx & 256) {
+                  // exact span: depth only (second half of the setup record: N, det, orig)
+                  const uint4* q4 = reinterpret_cast<const uint4*>(list + kk);
+                  const uint4 u2 = __ldg(q4 + 2), u3 = __ldg(q4 + 3);
+                  const V3 N{__uint_as_float(u2.y), __uint_as_float(u2.z), __uint_as_float(u2.w)};
+                  const float t = __fdiv_rn(__uint_as_float(u3.x), edge_fn(dx, dy, N));
+                  if (t >= kc.znear) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) |
+                                                   (unsigned long long)(((u3.w << 12) | (uint32_t)kk) + 1u);
+                    if (key < *zp) {
+                      atomicMin(zp, key);
+                      s_hits = 1;
+                    }
+                  }
+                } else {
+                  const Setup ss = load_setup(list + kk);
+                  raster_frag(ss, kk, dx, dy, zp, &s_hits);
+                }
               }
             }
           }
@@ -804,18 +912,22 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
             const float dx = s_dxp[px], dy = s_dyp[py];
             const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
             const float es = add(add(e0, e1), e2);
-            const float l1 = __fdiv_rn(e1, es), l2 = __fdiv_rn(e2, es);
-            const float l0 = sub(sub(1.0f, l1), l2);
+            const float ies = __fdividef(1.0f, es);
+            const float l1 = e1 * ies, l2 = e2 * ies;
+            const float l0 = 1.0f - l1 - l2;
             const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
             float no[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-              no[c] = add(add(mul(l0, a.vnorm[3 * i0 + c]), mul(l1, a.vnorm[3 * i1 + c])), mul(l2, a.vnorm[3 * i2 + c]));
+              no[c] = l0 * __ldg(a.vnorm + 3 * i0 + c) + l1 * __ldg(a.vnorm + 3 * i1 + c) + l2 * __ldg(a.vnorm + 3 * i2 + c);
             V3 n;
-            n.x = add(add(mul(sM[0], no[0]), mul(sM[1], no[1])), mul(sM[2], no[2]));
-            n.y = add(add(mul(sM[4], no[0]), mul(sM[5], no[1])), mul(sM[6], no[2]));
-            n.z = add(add(mul(sM[8], no[0]), mul(sM[9], no[1])), mul(sM[10], no[2]));
-            n = normalize(n);
+            n.x = sM[0] * no[0] + sM[1] * no[1] + sM[2] * no[2];
+            n.y = sM[4] * no[0] + sM[5] * no[1] + sM[6] * no[2];
+            n.z = sM[8] * no[0] + sM[9] * no[1] + sM[10] * no[2];
+            {
+              const float r = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
+              n.x *= r; n.y *= r; n.z *= r;
+            }
             V3 pp{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
             shade_t<NCH>(pp, n, rgb);
@@ -826,6 +938,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
 #pragma unroll
             for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
             hx0 = min(hx0, px); hx1 = max(hx1, px); hy0 = min(hy0, py); hy1 = max(hy1, py);
+            CT_COUNT(11, 1);
           };
           for (int base = warp * 32; base < npx; base += CT_BLOCK) {
             const int i = base + lane;
@@ -1173,11 +1286,11 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
 }
 
 #ifdef CT_PROFILE
-extern "C" int igi_debug_read_prof(unsigned long long* out16, int reset) {
+extern "C" int igi_debug_read_prof(unsigned long long* out32, int reset) {
   IGI_CUDA(cudaDeviceSynchronize());
-  IGI_CUDA(cudaMemcpyFromSymbol(out16, g_ct_prof, sizeof(unsigned long long) * 16));
+  IGI_CUDA(cudaMemcpyFromSymbol(out32, g_ct_prof, sizeof(unsigned long long) * 32));
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[32] = {0};
     IGI_CUDA(cudaMemcpyToSymbol(g_ct_prof, z, sizeof(z)));
   }
   return IGI_OK;

@@ -13,7 +13,7 @@ dev = task.device
 fp = torch.from_numpy(P["finger_pos"]).to(dev); fq = torch.from_numpy(P["finger_quat"]).to(dev)
 pp = torch.from_numpy(P["plug_pos"]).to(dev); pq = torch.from_numpy(P["plug_quat"]).to(dev)
 lib = _lib.load()
-out = (ctypes.c_ulonglong * 16)()
+out = (ctypes.c_ulonglong * 32)()
 for i in range(3):
     task.tactile_engine.render(fp, fq, pp, pq, obs_out=task.tactile_imgs)
 lib.igi_debug_read_prof(out, 1)
@@ -23,3 +23,10 @@ names = ["fetch/idle", "zinit", "rows+scan", "raster", "shade", "hblur", "vblur+
 v = np.array(list(out)[:9], dtype=np.float64)
 for n, x in zip(names, v):
     print(f"{n:12s} {100*x/v.sum():5.1f}%   {x/1e6:9.1f} Mcycles")
+c = list(out)
+nf = int((task.tactile_engine.contact_counts() > 0).sum().item())
+print(f"frames {nf}: per frame rows {c[9]/nf:.0f}, span pixels {c[10]/nf:.0f}, shaded px {c[11]/nf:.0f}, "
+      f"regions x chunks {c[12]/nf:.2f}, region px {c[13]/nf:.0f}, tris {c[14]/nf:.0f}")
+F = 3 * E
+print(f"geom per frame (all {F}): clusters kept {c[16]/F:.1f} of {c[17]/F:.1f}, faces in {c[18]/F:.0f}, front-facing {c[19]/F:.0f}, "
+      f"near gel {c[20]/F:.0f}, on screen {c[21]/F:.0f}, pass hi-z {c[22]/F:.0f} (incl. warp-queue recomputation), emitted {float(task.tactile_engine.contact_counts().clamp(min=0).float().mean()):.0f}")
