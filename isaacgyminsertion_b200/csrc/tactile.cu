@@ -621,9 +621,19 @@ struct ContactArgs {
   int sensors_per_env;
   int kmax;
 };
-constexpr int CT_BLOCK = 256;
+#ifndef CT_BLOCK_N
+#define CT_BLOCK_N 512
+#endif
+#ifndef CT_CTAS
+#define CT_CTAS 2
+#endif
+#ifndef CT_BUD_N
+#define CT_BUD_N 12288
+#endif
+constexpr int CT_BLOCK = CT_BLOCK_N;
 constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
-constexpr int CT_BUD_GRAY = 7936;    // region pixels (interior + halo) held in shared memory, 8 B each
+static_assert(CT_CHUNK % CT_BLOCK_N == 0, "CT_CHUNK must be a multiple of the block size");
+constexpr int CT_BUD_GRAY = CT_BUD_N;    // region pixels (interior + halo) held in shared memory, 8 B each
 constexpr int CT_BUD_RGB = 4096;     // three-channel path: + 24 B per pixel of difference / blur planes
 
 __device__ __forceinline__ int reflect101(int i, int n) {
@@ -639,29 +649,41 @@ __device__ __forceinline__ Setup load_setup(const Setup* p) {
   return u.s;
 }
 
-// Conservative pixel-column interval [xlo, xhi] of row `dy` that can lie inside the three edge planes.
-// An edge value is affine in the ray slope dx: e = dx*n.x + (dy*n.y - n.z); the bound -c/n.x is widened
-// by the worst-case rounding of the exactly-rounded per-pixel evaluation in cover(), then mapped to
-// pixel columns.  Only a superset is needed: every pixel of the interval still runs cover().
-__device__ __forceinline__ void row_span(const Setup& s, float dy, float sx0, float kx, int bx0, int bx1, int& xlo, int& xhi) {
-  float L = -1e30f, U = 1e30f;
-  bool empty = false;
+// Pixel-column interval [xlo, xhi] of row `dy` that can lie inside the three edge planes, and whether it
+// is exact.  An edge value is affine in the ray slope dx: e = dx*n.x + (dy*n.y - n.z).  Each edge value
+// is also a monotone function of the column even with its roundings (products and sums round
+// monotonically), so the covered columns of a row form ONE interval whose ends are the columns where
+// the edges switch.  A switching point is known up to +-m (worst-case rounding of the exactly-rounded
+// per-pixel evaluation in cover()); when no pixel centre of the row lies inside an uncertainty band that
+// matters, the interval is exact and its pixels need no edge test at all, only depth.  Otherwise the
+// conservative interval is returned with exact = false and every pixel runs cover().
+__device__ __forceinline__ void row_span(const Setup& s, float dy, float sx0, float kx, int bx0, int bx1, int& xlo,
+                                         int& xhi, bool& exact) {
+  float Llo = -1e30f, Lhi = -1e30f, Ulo = 1e30f, Uhi = 1e30f;
+  bool empty = false, sure = true;
   auto edge = [&](V3 n) {
     const float cy = dy * n.y;
     const float c = cy - n.z;
     const float eps = 2e-6f * (1.7f * fabsf(n.x) + fabsf(cy) + fabsf(n.z));
     if (n.x == 0.0f) {
       empty = empty || (c > eps);
+      sure = sure && (fabsf(c) > eps);
     } else {
-      const float inv = 1.0f / n.x;
-      const float b = -c * inv, m = eps * fabsf(inv);
-      if (n.x > 0.0f) U = fminf(U, b + m); else L = fmaxf(L, b - m);
+      const float inv = __fdividef(1.0f, n.x);
+      const float b = -c * inv, m = eps * fabsf(inv) + 1e-7f * fabsf(b);
+      if (n.x > 0.0f) { Uhi = fminf(Uhi, b + m); Ulo = fminf(Ulo, b - m); }
+      else { Llo = fmaxf(Llo, b - m); Lhi = fmaxf(Lhi, b + m); }
     }
   };
   edge(s.n0); edge(s.n1); edge(s.n2);
-  const float pl = fmaxf((L - sx0) * kx - 0.02f, -1.0f), pu = fminf((U - sx0) * kx + 0.02f, (float)TW);
-  xlo = max(bx0, (int)ceilf(pl));
-  xhi = empty ? -1 : min(bx1, (int)floorf(pu));
+  const float lim_lo = -1.0f, lim_hi = (float)TW;
+  const int loA = (int)ceilf(fminf(fmaxf((Llo - sx0) * kx - 0.002f, lim_lo), lim_hi));
+  const int loB = (int)ceilf(fminf(fmaxf((Lhi - sx0) * kx + 0.002f, lim_lo), lim_hi));
+  const int hiA = (int)floorf(fminf(fmaxf((Uhi - sx0) * kx + 0.002f, lim_lo), lim_hi));
+  const int hiB = (int)floorf(fminf(fmaxf((Ulo - sx0) * kx - 0.002f, lim_lo), lim_hi));
+  xlo = max(bx0, loA);
+  xhi = empty ? -1 : min(bx1, hiA);
+  exact = sure && loB <= xlo && hiB >= xhi;
 }
 
 // One fragment: exact coverage + depth, GL_LESS against what the shared z-buffer holds (it starts
@@ -679,8 +701,21 @@ __device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, flo
   }
 }
 
+// Fragment of an exact span: inside by construction, only depth (N, det) and the z test.
+__device__ __forceinline__ void raster_frag_depth(V3 N, float det, uint32_t orig, int k, float dx, float dy,
+                                                  unsigned long long* zp, int* s_hits) {
+  const float t = __fdiv_rn(det, edge_fn(dx, dy, N));
+  if (!(t >= kc.znear)) return;
+  const unsigned long long key =
+      ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(((orig << 12) | (uint32_t)k) + 1u);
+  if (key < *zp) {
+    atomicMin(zp, key);
+    *s_hits = 1;
+  }
+}
+
 template <int NCH>
-__global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(ContactArgs a) {
+__global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(ContactArgs a) {
 #ifdef CT_PROFILE
   long long t_prof = clock64();
 #endif
@@ -824,25 +859,22 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
               const int bx1 = min((int)((s.bbox >> 16) & 255u), cx1);
               py = by0 + (i - s_off[lo]);
               const float dy = s_dyp[py];
-              row_span(s, dy, span_x0, span_kx, bx0, bx1, xlo, xhi);
-              // Each edge value is a monotone function of the column even with its roundings (products
-              // and sums round monotonically), so the covered columns of a row form ONE interval.
-              // Walk the conservative ends inwards to the exact ends (normally 0-1 steps): the
-              // pixels in between then need no edge test at all, only depth.
-              auto inside = [&](int px) {
-                const float dx = s_dxp[px];
-                return edge_in(edge_fn(dx, dy, s.n0), s.n0) && edge_in(edge_fn(dx, dy, s.n1), s.n1) &&
-                       edge_in(edge_fn(dx, dy, s.n2), s.n2);
-              };
-              int tries = 0;
-              while (xlo <= xhi && tries < 3 && !inside(xlo)) { ++xlo; ++tries; }
-              bool ok = xlo > xhi || tries < 3 || inside(xlo);
-              tries = 0;
-              while (xlo < xhi && tries < 3 && !inside(xhi)) { --xhi; ++tries; }
-              ok = ok && (xlo >= xhi || tries < 3 || inside(xhi));
-              exact = ok ? 1 : 0;
+              bool ex;
+              row_span(s, dy, span_x0, span_kx, bx0, bx1, xlo, xhi, ex);
+              exact = ex ? 1 : 0;
+              // most spans are one or two pixels: those are done right here by the lane that owns the row
+              unsigned long long* zrow = s_z + (py - ry0) * RW - rx0;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int px = xlo + u;
+                if (px <= xhi) {
+                  if (ex) raster_frag_depth(s.N, s.det, s.orig, k, s_dxp[px], dy, zrow + px, &s_hits);
+                  else raster_frag(s, k, s_dxp[px], dy, zrow + px, &s_hits);
+                }
+              }
+              xlo += 2;
             }
-            // The 32 row spans of the warp are flattened into one pixel list (warp scan of the span
+            // What is left of the longer spans is flattened into one pixel list (warp scan of the
             // lengths) and dealt out one pixel per lane, so lanes stay busy whatever the span lengths.
             const int len = max(xhi - xlo + 1, 0);
             int excl = len;
@@ -873,15 +905,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
                   const uint4* q4 = reinterpret_cast<const uint4*>(list + kk);
                   const uint4 u2 = __ldg(q4 + 2), u3 = __ldg(q4 + 3);
                   const V3 N{__uint_as_float(u2.y), __uint_as_float(u2.z), __uint_as_float(u2.w)};
-                  const float t = __fdiv_rn(__uint_as_float(u3.x), edge_fn(dx, dy, N));
-                  if (t >= kc.znear) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) |
-                                                   (unsigned long long)(((u3.w << 12) | (uint32_t)kk) + 1u);
-                    if (key < *zp) {
-                      atomicMin(zp, key);
-                      s_hits = 1;
-                    }
-                  }
+                  raster_frag_depth(N, __uint_as_float(u3.x), u3.w, kk, dx, dy, zp, &s_hits);
                 } else {
                   const Setup ss = load_setup(list + kk);
                   raster_frag(ss, kk, dx, dy, zp, &s_hits);
@@ -974,59 +998,87 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? 3 : 1) tac_contact(Contac
         }
         __syncthreads();
         CT_T(4);
-        // --- 7-tap horizontal pass over the interior columns (BORDER_REFLECT_101 at the image edge)
-        const int iw = ix1 - tx + 1;
-        for (int ry = warp; ry < RH; ry += NW) {
-          const int py = ry0 + ry;
-          if (py < 0 || py >= TH) continue;
-          for (int lx = lane; lx < iw; lx += 32) {
-            const int px = tx + lx;
-            float acc[NCH];
+        // --- 7-tap horizontal pass over the interior columns (BORDER_REFLECT_101 at the image edge).
+        // A thread produces 4 neighbouring outputs from one 10-value window.
+        const int iw = ix1 - tx + 1, ih = iy1 - ty + 1;
+        {
+          const int nqx = (iw + 3) >> 2;
+          const uint32_t inv_q = 0xffffffffu / (uint32_t)nqx + 1u;
+          for (int it = tid; it < RH * nqx; it += CT_BLOCK) {
+            const int ry = (int)__umulhi((uint32_t)it, inv_q), qx = it - ry * nqx;
+            const int py = ry0 + ry;
+            if (py < 0 || py >= TH) continue;
+            const int px0 = tx + 4 * qx;
+            float win[10][NCH];
+            const bool inner = px0 >= HALO && px0 + 3 + HALO < TW;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+            for (int j = 0; j < 10; ++j) {
+              const int sx = (inner ? px0 + j - HALO : reflect101(px0 + j - HALO, TW)) - rx0;
+              const float* dp = &s_diff[(ry * RW + min(sx, RW - 1)) * DS];
 #pragma unroll
-            for (int k = -3; k <= 3; ++k) {
-              const int sx = reflect101(px + k, TW) - rx0;
-              const float w = kc.gauss[k + 3];
-              const float* dp = &s_diff[(ry * RW + sx) * DS];
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, dp[c], acc[c]);
+              for (int c = 0; c < NCH; ++c) win[j][c] = dp[c];
             }
-            float* hp = &s_h[(ry * RW + (px - rx0)) * DS];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) hp[c] = acc[c];
+            for (int o = 0; o < 4; ++o) {
+              if (px0 + o > ix1) break;
+              float acc[NCH];
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 7; ++k) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) acc[c] = fmaf(kc.gauss[k], win[o + k][c], acc[c]);
+              }
+              float* hp = &s_h[(ry * RW + (px0 + o - rx0)) * DS];
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) hp[c] = acc[c];
+            }
           }
         }
         __syncthreads();
         CT_T(5);
-        // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8)).  The per-channel change
-        // (colour - bg_real, 10 bits each) is left in the pixel's dead low word for the obs stage.
-        for (int ly = warp; ly <= iy1 - ty; ly += NW) {
-          const int py = ty + ly;
-          for (int lx = lane; lx < iw; lx += 32) {
-            const int px = tx + lx;
-            float acc[NCH];
+        // --- vertical pass, + bg_real, clip, truncate (numpy astype(uint8)); 4 rows of a column per
+        // thread.  The per-channel change (colour - bg_real, 10 bits each) is left in the pixel's dead
+        // low word for the obs stage.
+        {
+          const int nqy = (ih + 3) >> 2;
+          const uint32_t inv_w = 0xffffffffu / (uint32_t)iw + 1u;
+          for (int it = tid; it < nqy * iw; it += CT_BLOCK) {
+            const int qy = (int)__umulhi((uint32_t)it, inv_w), lx = it - qy * iw;
+            const int px = tx + lx, py0 = ty + 4 * qy;
+            float win[10][NCH];
+            const bool inner = py0 >= HALO && py0 + 3 + HALO < TH;
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+            for (int j = 0; j < 10; ++j) {
+              const int sy = (inner ? py0 + j - HALO : reflect101(py0 + j - HALO, TH)) - ry0;
+              const float* hp = &s_h[(min(sy, RH - 1) * RW + (px - rx0)) * DS];
 #pragma unroll
-            for (int k = -3; k <= 3; ++k) {
-              const int sy = reflect101(py + k, TH) - ry0;
-              const float w = kc.gauss[k + 3];
-              const float* hp = &s_h[(sy * RW + (px - rx0)) * DS];
-#pragma unroll
-              for (int c = 0; c < NCH; ++c) acc[c] = fmaf(w, hp[c], acc[c]);
+              for (int c = 0; c < NCH; ++c) win[j][c] = hp[c];
             }
-            const size_t o = ((size_t)py * TW + px) * 3;
-            uint32_t packed = 0;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const int b = (int)__ldg(bgr + o + c);
-              const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)b, kc.clip_lo, kc.clip_hi);
-              const int q = (int)(uint8_t)v;
-              col[o + c] = (uint8_t)q;
-              packed |= (uint32_t)(q - b + 256) << (10 * c);
+            for (int o = 0; o < 4; ++o) {
+              const int py = py0 + o;
+              if (py > iy1) break;
+              float acc[NCH];
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+#pragma unroll
+              for (int k = 0; k < 7; ++k) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) acc[c] = fmaf(kc.gauss[k], win[o + k][c], acc[c]);
+              }
+              const size_t off = ((size_t)py * TW + px) * 3;
+              uint32_t packed = 0;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const int bb = (int)__ldg(bgr + off + c);
+                const float v = clampf(acc[NCH == 1 ? 0 : c] + (float)bb, kc.clip_lo, kc.clip_hi);
+                const int q = (int)(uint8_t)v;
+                col[off + c] = (uint8_t)q;
+                packed |= (uint32_t)(q - bb + 256) << (10 * c);
+              }
+              if (NCH == 1) reinterpret_cast<uint32_t*>(s_z)[2 * ((py - ry0) * RW + (px - rx0))] = packed;
             }
-            if (NCH == 1) reinterpret_cast<uint32_t*>(s_z)[2 * ((py - ry0) * RW + (px - rx0))] = packed;
           }
         }
         CT_T(6);
@@ -1278,7 +1330,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
       IGI_CUDA(cudaFuncSetAttribute(tac_contact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rgb));
       attr_set = true;
     }
-    if (g_gray) tac_contact<1><<<min(F, sms * 3), CT_BLOCK, smem_gray, s>>>(ca);
+    if (g_gray) tac_contact<1><<<min(F, sms * CT_CTAS), CT_BLOCK, smem_gray, s>>>(ca);
     else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(ca);
     IGI_CHECK_LAUNCH("tac_contact");
   }

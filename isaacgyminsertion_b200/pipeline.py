@@ -1,0 +1,106 @@
+"""Host-buffer front end of the observation path.
+
+`HostObsPipeline` is the call a user with HOST data makes: every `step()` takes the step's
+inputs as (pinned) host tensors — fingertip / plug poses and the external camera's depth +
+segmentation images, i.e. what the reference task reads from IsaacGym each step
+(factory_task_insertion.py:481-484, 918-919) — enqueues upload, kernels and download, and
+returns a `PendingObs` whose `.wait()` yields the packed observation rows
+`[tactile 3*2048 | pcl 2400]` of that step in pinned host memory.
+
+Copies and kernels run on three streams (upload, compute, download) over a ring of SLOTS device
+input / device output / host output buffers, so in steady state the H2D copy of step i+1 and the
+D2H copy of step i-1 overlap the kernels of step i.  A result stays valid until SLOTS more steps
+have been submitted; host input buffers must not be modified until the step's `.wait()` returned
+(or `uploaded.synchronize()`).
+"""
+import torch
+
+
+SLOTS = 3
+
+
+class PendingObs:
+    def __init__(self, tensor, event, uploaded):
+        self.tensor, self.event, self.uploaded = tensor, event, uploaded
+
+    def wait(self):
+        self.event.synchronize()
+        return self.tensor
+
+
+class HostObsPipeline:
+    def __init__(self, task, sampler_socket_every_step=False):
+        self.task = task
+        dev = task.device
+        self.dev = dev
+        self.s_up = torch.cuda.Stream(device=dev)
+        self.s_down = torch.cuda.Stream(device=dev)
+        N = task.num_envs
+        H, W = task.res[1], task.res[0]
+        f32, i32 = torch.float32, torch.int32
+
+        def mk():
+            return dict(fpos=torch.empty((N, 3, 3), dtype=f32, device=dev), fquat=torch.empty((N, 3, 4), dtype=f32, device=dev),
+                        ppos=torch.empty((N, 3), dtype=f32, device=dev), pquat=torch.empty((N, 4), dtype=f32, device=dev),
+                        depth=torch.empty((N, H, W), dtype=f32, device=dev), seg=torch.empty((N, H, W), dtype=i32, device=dev))
+        self.d_in = [mk() for _ in range(SLOTS)]
+        self.d_out = [torch.empty_like(task.obs_packed) for _ in range(SLOTS)]
+        self.h_out = [torch.empty(task.obs_packed.shape, dtype=f32).pin_memory() for _ in range(SLOTS)]
+        self.ev_up = [torch.cuda.Event() for _ in range(SLOTS)]      # inputs of slot ready on the device
+        self.ev_done = [torch.cuda.Event() for _ in range(SLOTS)]    # kernels of slot finished (inputs free, output snapshot ready)
+        self.ev_down = [torch.cuda.Event() for _ in range(SLOTS)]    # host copy of slot complete
+        self.i = 0
+        self.socket_every_step = sampler_socket_every_step
+        N_ = N
+        self._ones = torch.ones(N_, dtype=torch.bool, device=dev)
+        self._zeros = torch.zeros(N_, dtype=torch.bool, device=dev)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in[0].values())
+        self.d2h_bytes = self.h_out[0].numel() * 4
+
+    @torch.no_grad()
+    def step(self, fpos, fquat, ppos, pquat, depth, seg, update=None):
+        """Submit one step (host tensors, ideally pinned); never blocks the host.  Returns a
+        PendingObs for this step's observations."""
+        task, i = self.task, self.i
+        slot = i % SLOTS
+        cur = torch.cuda.current_stream(self.dev)
+        # upload into the slot once the kernels that last read it (step i-SLOTS) are done
+        with torch.cuda.stream(self.s_up):
+            if i >= SLOTS:
+                self.s_up.wait_event(self.ev_done[slot])
+            d = self.d_in[slot]
+            for k, src in (("fpos", fpos), ("fquat", fquat), ("ppos", ppos), ("pquat", pquat), ("depth", depth), ("seg", seg)):
+                d[k].copy_(src.reshape(d[k].shape), non_blocking=True)
+            self.ev_up[slot].record(self.s_up)
+        # kernels
+        cur.wait_event(self.ev_up[slot])
+        if i >= SLOTS:
+            cur.wait_event(self.ev_down[slot])       # the download that read d_out[slot] is done
+        task.left_finger_pos, task.right_finger_pos, task.middle_finger_pos = d["fpos"][:, 0], d["fpos"][:, 1], d["fpos"][:, 2]
+        task.left_finger_quat, task.right_finger_quat, task.middle_finger_quat = d["fquat"][:, 0], d["fquat"][:, 1], d["fquat"][:, 2]
+        task.plug_pos, task.plug_quat = d["ppos"], d["pquat"]
+        task.cam_renders, task.seg_renders = d["depth"], d["seg"]
+        up = self._ones if update is None else update
+        if task.tactile:
+            task.update_tactile(up, up)
+        if task.pcl_cam:
+            if self.socket_every_step:
+                task._socket_pending = True
+                task.got_socket.zero_()
+            task.update_external_cam(up, up, up, self._zeros, self._zeros)
+        self.d_out[slot].copy_(task.obs_packed)
+        self.ev_done[slot].record(cur)
+        # download
+        with torch.cuda.stream(self.s_down):
+            self.s_down.wait_event(self.ev_done[slot])
+            self.h_out[slot].copy_(self.d_out[slot], non_blocking=True)
+            self.ev_down[slot].record(self.s_down)
+        self.i += 1
+        self._last = PendingObs(self.h_out[slot], self.ev_down[slot], self.ev_up[slot])
+        return self._last
+
+    def flush(self):
+        """Wait for the last submitted step and return its host observations."""
+        if self.i == 0:
+            return None
+        return self._last.wait()
