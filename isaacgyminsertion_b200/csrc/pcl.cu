@@ -345,75 +345,168 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
   }
 }
 
-// The m-1 dependent picks of one warp-resident task with PPL points per lane (n <= 32*PPL).
-// Returns after filling sel[0..m).  Once the winning distance is 0 (all points already picked, or
-// only duplicates left) or nothing is a candidate, the minima cannot change any more and every
-// later pick repeats the same index, so the loop stops there and the tail is filled directly.
+// ---- resident FPS: tasks of up to FW_COOP_MAXN points --------------------------------------------
+// One CTA = FW_WARPS warps owns FW_WARPS consecutive tasks.  A task of up to FW_MAXN points is run by
+// ONE warp (points in the warp's shared-memory planes, running minima and tie keys in registers, the
+// arg-max is two REDUX instructions, no block barrier); a task of FW_MAXN+1 .. FW_COOP_MAXN points is run
+// by ALL warps of the CTA together first (one barrier per pick), so that the few long tasks get four
+// warps' worth of issue slots instead of becoming the tail of the launch.  Same selection rule as
+// fps_kernel and oracle/fps.py.
+//
+// Inner loop, branch free: a point that can never be picked (|p|^2 <= 1e-3, or beyond n) keeps a running
+// minimum of -1, distances are >= 0, so a float max over min(d, temp) ignores it; the winner among equal
+// distances is then the largest tie key among the points whose minimum equals the max.
+constexpr int FW_WARPS = 4, FW_MAXN = 384, FW_COOP_MAXN = 1024, FW_COOP_PPL = FW_COOP_MAXN / (FW_WARPS * 32);
+
+__device__ __forceinline__ uint32_t fps_tie_key(int k, int lg, uint32_t bmask) {
+  const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
+  return ~((rev << 16) | (uint32_t)k);
+}
+
+// PPL points per lane, point index of slot i = first + stride * i
 template <int PPL>
-__device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy, const float* sz, int n, int m,
-                                              int lane, unsigned short* sel) {
+__device__ __forceinline__ void fps_init_state(const float* sx, const float* sy, const float* sz, int n, int first,
+                                               int stride, float* temp, uint32_t* lokey) {
   int lg = 31 - __clz(n);
   if (lg > 9) lg = 9;
   const uint32_t bmask = (1u << lg) - 1u;
-  float temp[PPL];
-  uint32_t lokey[PPL];  // 0 = not a candidate
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
-    const int k = lane + 32 * i;
-    temp[i] = 1e10f;
+    const int k = first + stride * i;
+    temp[i] = -1.0f;
     lokey[i] = 0u;
     if (k < n) {
       const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
       const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
       if (mag > 1e-3f) {
-        const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
-        lokey[i] = ~((rev << 16) | (uint32_t)k);
+        temp[i] = 1e10f;
+        lokey[i] = fps_tie_key(k, lg, bmask);
       }
     }
   }
+}
+
+// one pick, per-thread part: update the minima against point `old`, return the thread's best minimum
+template <int PPL>
+__device__ __forceinline__ float fps_update(const float* sx, const float* sy, const float* sz, int old, int first,
+                                            int stride, float* temp) {
+  const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+  float best = -1.0f;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const int k = first + stride * i;   // planes are padded: reads beyond n are harmless (min with -1 stays -1)
+    const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float d2 = fminf(d, temp[i]);
+    temp[i] = d2;
+    best = fmaxf(best, d2);
+  }
+  return best;
+}
+
+template <int PPL>
+__device__ __forceinline__ uint32_t fps_tie(const float* temp, const uint32_t* lokey, int wbest) {
+  uint32_t blo = 0u;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i)
+    if (__float_as_int(temp[i]) == wbest) blo = max(blo, lokey[i]);
+  return blo;
+}
+
+// The m-1 dependent picks of one warp-resident task.  Fills sel[0..m).  Once the winning distance is 0
+// (all points already picked, or only duplicates left) or nothing is a candidate, the minima cannot
+// change any more and every later pick repeats the same index, so the loop stops there.
+template <int PPL>
+__device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy, const float* sz, int n, int m,
+                                               int lane, unsigned short* sel) {
+  float temp[PPL];
+  uint32_t lokey[PPL];
+  fps_init_state<PPL>(sx, sy, sz, n, lane, 32, temp, lokey);
   int old = 0;
   if (lane == 0) sel[0] = 0;
   int j = 1;
   for (; j < m; ++j) {
-    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-    uint32_t bhi = 0, blo = 0;
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) {
-      if (lokey[i] != 0u) {
-        const int k = lane + 32 * i;
-        const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float d2 = fminf(d, temp[i]);
-        temp[i] = d2;
-        const uint32_t hi = __float_as_uint(d2) + 1u;
-        if (hi > bhi || (hi == bhi && lokey[i] > blo)) { bhi = hi; blo = lokey[i]; }
-      }
-    }
-    const uint32_t whi = __reduce_max_sync(0xffffffffu, bhi);
-    const uint32_t wlo = __reduce_max_sync(0xffffffffu, (bhi == whi) ? blo : 0u);
-    old = (whi == 0) ? 0 : (int)((~wlo) & 0xffffu);
+    const float best = fps_update<PPL>(sx, sy, sz, old, lane, 32, temp);
+    const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));   // floats >= 0 order as ints; -1 < 0
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
+    old = (wb < 0) ? 0 : (int)((~wlo) & 0xffffu);
     if (lane == 0) sel[j] = (unsigned short)old;
-    if (whi <= 1u) { ++j; break; }
+    if (wb <= 0) { ++j; break; }
   }
   for (int i = j + lane; i < m; i += 32) sel[i] = (unsigned short)old;
 }
 
-// Warp-per-task FPS for the common small clouds (n <= FW_MAXN): the task's points sit in a
-// per-warp SoA slice of shared memory, running minimum distances and tie keys in registers,
-// the arg-max is two REDUX instructions, no block barrier anywhere.  Same selection rule as
-// fps_kernel (and oracle/fps.py).
-constexpr int FW_WARPS = 4, FW_MAXN = 512, FW_PPL = FW_MAXN / 32;
-
 __global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float* pts, int64_t task_stride,
-                                                                 const int32_t* count, const int32_t* any,
-                                                                 int64_t count_stride, int n_fixed, int n_tasks,
-                                                                 int m, float* out_pts, int64_t out_stride,
-                                                                 int32_t* out_idx) {
-  // dynamic smem: FW_WARPS x [3][FW_MAXN] f32 point planes, then FW_WARPS x m selected indices (u16)
+                                                                    const int32_t* count, const int32_t* any,
+                                                                    int64_t count_stride, int n_fixed, int n_tasks,
+                                                                    int m, float* out_pts, int64_t out_stride,
+                                                                    int32_t* out_idx) {
+  // dynamic smem: [3][FW_COOP_MAXN] f32 point planes (a warp task uses its own FW_MAXN... slice of every
+  // plane set, see below), then FW_WARPS x m selected indices (u16)
   extern __shared__ __align__(16) unsigned char fw_smem[];
-  float* s_p = reinterpret_cast<float*>(fw_smem);
-  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * FW_WARPS * 3 * FW_MAXN);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PLANE = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
+  float* s_p = reinterpret_cast<float*>(fw_smem);          // [3][PLANE]
+  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * 3 * PLANE);
+  __shared__ int2 s_cand[2][FW_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- long tasks of this CTA's group: all warps together, one after the other
+  for (int t = 0; t < FW_WARPS; ++t) {
+    const int task = blockIdx.x * FW_WARPS + t;
+    if (task >= n_tasks) break;
+    const int n = count ? count[(size_t)task * count_stride] : n_fixed;
+    if (n <= FW_MAXN || n > FW_COOP_MAXN) continue;
+    if (any && any[(size_t)task * count_stride] == 0) continue;   // written as zeros by its warp below
+    float* sx = s_p;
+    float* sy = sx + PLANE;
+    float* sz = sy + PLANE;
+    __syncthreads();
+    const float* src = pts + (size_t)task * task_stride;
+    for (int i = tid; i < 3 * n; i += FW_WARPS * 32) {
+      const int k = i / 3, c = i - 3 * k;
+      s_p[c * PLANE + k] = src[i];
+    }
+    for (int k = n + tid; k < FW_COOP_MAXN; k += FW_WARPS * 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
+    __syncthreads();
+    float temp[FW_COOP_PPL];
+    uint32_t lokey[FW_COOP_PPL];
+    fps_init_state<FW_COOP_PPL>(sx, sy, sz, n, tid, FW_WARPS * 32, temp, lokey);
+    float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
+    int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
+    int old = 0;
+    if (tid == 0) {
+      if (idst) idst[0] = 0;
+      if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
+    }
+    int j = 1;
+    for (; j < m; ++j) {
+      const float best = fps_update<FW_COOP_PPL>(sx, sy, sz, old, tid, FW_WARPS * 32, temp);
+      const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+      const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<FW_COOP_PPL>(temp, lokey, wb));
+      if (lane == 0) s_cand[j & 1][warp] = make_int2(wb, (int)wlo);
+      __syncthreads();
+      int fb = -2;
+      uint32_t flo = 0u;
+#pragma unroll
+      for (int w = 0; w < FW_WARPS; ++w) {
+        const int2 c = s_cand[j & 1][w];
+        if (c.x > fb || (c.x == fb && (uint32_t)c.y > flo)) { fb = c.x; flo = (uint32_t)c.y; }
+      }
+      old = (fb < 0) ? 0 : (int)((~flo) & 0xffffu);
+      if (tid == 0) {
+        if (idst) idst[j] = old;
+        if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
+      }
+      if (fb <= 0) { ++j; break; }
+    }
+    for (int i = j + tid; i < m; i += FW_WARPS * 32) {
+      if (idst) idst[i] = old;
+      if (dst) { dst[i * 3 + 0] = sx[old]; dst[i * 3 + 1] = sy[old]; dst[i * 3 + 2] = sz[old]; }
+    }
+  }
+  __syncthreads();
+
+  // ---- one task per warp
   const int task = blockIdx.x * FW_WARPS + warp;
   if (task >= n_tasks) return;
   const int n = count ? count[(size_t)task * count_stride] : n_fixed;
@@ -427,22 +520,21 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float*
     }
     return;
   }
-  if (n > FW_MAXN) return;  // fps_kernel handles it
-  float* sx = s_p + (size_t)warp * 3 * FW_MAXN;
-  float* sy = sx + FW_MAXN;
-  float* sz = sy + FW_MAXN;
+  if (n > FW_MAXN) return;  // done above, or fps_kernel's
+  float* sx = s_p + (size_t)warp * FW_MAXN;
+  float* sy = sx + PLANE;
+  float* sz = sy + PLANE;
   unsigned short* sel = s_sel_all + warp * m;
   const float* src = pts + (size_t)task * task_stride;
   for (int i = lane; i < 3 * n; i += 32) {
-    const float v = src[i];
     const int k = i / 3, c = i - 3 * k;
-    sx[c * FW_MAXN + k] = v;
+    sx[c * PLANE + k] = src[i];
   }
+  for (int k = n + lane; k < FW_MAXN; k += 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
   __syncwarp();
   if (n <= 128) fps_warp_picks<4>(sx, sy, sz, n, m, lane, sel);
   else if (n <= 256) fps_warp_picks<8>(sx, sy, sz, n, m, lane, sel);
-  else if (n <= 384) fps_warp_picks<12>(sx, sy, sz, n, m, lane, sel);
-  else fps_warp_picks<FW_PPL>(sx, sy, sz, n, m, lane, sel);
+  else fps_warp_picks<FW_MAXN / 32>(sx, sy, sz, n, m, lane, sel);
   __syncwarp();
   for (int i = lane; i < m; i += 32) {
     const int k = sel[i];
@@ -516,10 +608,11 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nmax = count ? task_stride / 3 : n_fixed;
   IGI_REQUIRE(nmax <= 0xffff, "igi_fps: at most 65535 points per task");
-  const size_t warp_smem = sizeof(float) * FW_WARPS * 3 * FW_MAXN + (size_t)FW_WARPS * m * 2;
+  constexpr int kPlane = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
+  const size_t warp_smem = sizeof(float) * 3 * kPlane + (size_t)FW_WARPS * m * 2;
   const bool warp_ok = warp_smem <= 28 * 1024;  // keeps 8 CTAs (32 task warps) per SM
-  const bool need_block = !warp_ok || nmax > FW_MAXN;
-  const bool need_warp = warp_ok && (count != nullptr || n_fixed <= FW_MAXN);
+  const bool need_block = !warp_ok || nmax > FW_COOP_MAXN;
+  const bool need_warp = warp_ok && (count != nullptr || n_fixed <= FW_COOP_MAXN);
   if (need_warp) {
     static bool warp_attr = false;
     if (!warp_attr) {
@@ -545,7 +638,7 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
     const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
     const int grid = n_tasks < sms * per_sm ? n_tasks : sms * per_sm;
     fps_kernel<<<grid, kFpsBlock, smem, st>>>(pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m,
-                                              out_pts, out_stride, out_idx, need_warp ? FW_MAXN + 1 : 0);
+                                              out_pts, out_stride, out_idx, need_warp ? FW_COOP_MAXN + 1 : 0);
     IGI_CHECK_LAUNCH("fps_kernel");
   }
   return IGI_OK;
