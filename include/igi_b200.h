@@ -25,6 +25,8 @@ extern "C" {
 
 int igi_version(void);
 const char* igi_last_error(void);
+/* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
+long long igi_launch_count(void);
 
 /* --------------------------------------------------------------------------
  * (P) external-camera point cloud
@@ -195,6 +197,10 @@ int igi_tactile_gel_precompute(const float* gel_tris, int n_tris, uint64_t* scra
  * mask, flipud, crop, INTER_AREA resize, gray (task :546-574). */
 int igi_tactile_render(const IgiTactileMeshes* meshes, const IgiTactileStatic* st, const IgiTactileFrames* frames,
                        const IgiTactileScratch* scratch, const IgiTactileOut* out, void* stream);
+
+/* Test hook: cap the pixels (interior + blur halo) one shared-memory region of the contact kernel may
+ * hold, so small inputs exercise the multi-region path.  0 restores the built-in budget. */
+int igi_tactile_set_region_budget(int pixels);
 
 /* K3 alone: color (F,H,W,3) u8 -> obs.  Replaces factory_task_insertion.py:546-574. */
 int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,

@@ -40,7 +40,9 @@ def load():
     lib.igi_last_error.restype = _c.c_char_p
     for name in declared_symbols():
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
-        if name not in ("igi_last_error",):
+        if name == "igi_launch_count":
+            fn.restype = _c.c_longlong
+        elif name not in ("igi_last_error",):
             fn.restype = _c.c_int
     _lib = lib
     return lib

@@ -10,6 +10,7 @@
 #define IGI_ERR_UNSUPPORTED (-3)
 
 void igi_set_error(const char* fmt, ...);
+void igi_count_launch();  // every kernel launch of the library goes through IGI_CHECK_LAUNCH
 
 #define IGI_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -22,6 +23,7 @@ void igi_set_error(const char* fmt, ...);
 // Launch errors are surfaced without synchronising (callee never syncs).
 #define IGI_CHECK_LAUNCH(name)                                              \
   do {                                                                      \
+    igi_count_launch();                                                     \
     cudaError_t e__ = cudaPeekAtLastError();                                \
     if (e__ != cudaSuccess) {                                               \
       igi_set_error("%s: %s", name, cudaGetErrorString(e__));               \

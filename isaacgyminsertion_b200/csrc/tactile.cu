@@ -620,6 +620,7 @@ struct ContactArgs {
   int64_t obs_env_stride, obs_sensor_stride;
   int sensors_per_env;
   int kmax;
+  int budget;                // region pixel budget (<= the compiled one)
 };
 #ifndef CT_BLOCK_N
 #define CT_BLOCK_N 512
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     // cut the window into the fewest sub-windows whose region (interior + halo) fits the budget
     const int ww = wx1 - wx0 + 1, wh = wy1 - wy0 + 1;
     int nsx = 1, nsy = 1;
-    while (((ww + nsx - 1) / nsx + 2 * HALO) * ((wh + nsy - 1) / nsy + 2 * HALO) > BUD) {
+    while (((ww + nsx - 1) / nsx + 2 * HALO) * ((wh + nsy - 1) / nsy + 2 * HALO) > a.budget) {
       if ((ww + nsx - 1) / nsx >= (wh + nsy - 1) / nsy) ++nsx; else ++nsy;
     }
     const int tw = (ww + nsx - 1) / nsx, th = (wh + nsy - 1) / nsy;
@@ -1003,9 +1004,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int iw = ix1 - tx + 1, ih = iy1 - ty + 1;
         {
           const int nqx = (iw + 3) >> 2;
-          const uint32_t inv_q = 0xffffffffu / (uint32_t)nqx + 1u;
+          const uint32_t inv_q = 0xffffffffu / (uint32_t)nqx + 1u;   // wraps to 0 for nqx == 1
           for (int it = tid; it < RH * nqx; it += CT_BLOCK) {
-            const int ry = (int)__umulhi((uint32_t)it, inv_q), qx = it - ry * nqx;
+            const int ry = nqx == 1 ? it : (int)__umulhi((uint32_t)it, inv_q), qx = it - ry * nqx;
             const int py = ry0 + ry;
             if (py < 0 || py >= TH) continue;
             const int px0 = tx + 4 * qx;
@@ -1042,9 +1043,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         // low word for the obs stage.
         {
           const int nqy = (ih + 3) >> 2;
-          const uint32_t inv_w = 0xffffffffu / (uint32_t)iw + 1u;
+          const uint32_t inv_w = 0xffffffffu / (uint32_t)iw + 1u;    // wraps to 0 for iw == 1
           for (int it = tid; it < nqy * iw; it += CT_BLOCK) {
-            const int qy = (int)__umulhi((uint32_t)it, inv_w), lx = it - qy * iw;
+            const int qy = iw == 1 ? it : (int)__umulhi((uint32_t)it, inv_w), lx = it - qy * iw;
             const int px = tx + lx, py0 = ty + 4 * qy;
             float win[10][NCH];
             const bool inner = py0 >= HALO && py0 + 3 + HALO < TH;
@@ -1184,6 +1185,13 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
 // C-ABI
 // =============================================================================================
 static int g_gray = 0;  // mirrors kc.gray of the last igi_tactile_set_sensor (one device per process)
+static int g_region_budget = 0;  // 0 = compiled budget
+
+extern "C" int igi_tactile_set_region_budget(int pixels) {
+  IGI_REQUIRE(pixels == 0 || pixels >= (2 * HALO + 1) * (2 * HALO + 1), "igi_tactile_set_region_budget: need 0 or >= 49 pixels");
+  g_region_budget = pixels;
+  return IGI_OK;
+}
 
 extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
   IGI_REQUIRE(p != nullptr, "igi_tactile_set_sensor: null params");
@@ -1319,6 +1327,10 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   ca.obs_env_stride = out->obs_env_stride; ca.obs_sensor_stride = out->obs_sensor_stride;
   ca.sensors_per_env = fr->sensors_per_env;
   ca.kmax = sc->kmax;
+  {
+    const int compiled = g_gray ? CT_BUD_GRAY : CT_BUD_RGB;
+    ca.budget = g_region_budget > 0 && g_region_budget < compiled ? g_region_budget : compiled;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

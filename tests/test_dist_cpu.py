@@ -1,0 +1,66 @@
+"""Multi-process host logic of the observation gather (gloo, world_size 2, CPU)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from isaacgyminsertion_b200 import dist as igdist
+
+
+def test_env_slices_partition_the_envs():
+    for total in (1, 7, 8, 4096, 4099):
+        for world in (1, 2, 3, 8):
+            parts = [igdist.env_slice(total, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == total
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, row, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, lr, w = igdist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    lo, hi = igdist.env_slice(total, rank, world)
+    # packed rows carry the global env id so order and ownership can be checked after the gather
+    local = torch.arange(lo, hi, dtype=torch.float32)[:, None] * 10 + torch.arange(row, dtype=torch.float32)[None]
+    got = igdist.gather_observations(local, total_envs=total)
+    want = torch.arange(total, dtype=torch.float32)[:, None] * 10 + torch.arange(row, dtype=torch.float32)[None]
+    q.put((rank, bool(torch.equal(got, want)), tuple(got.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 9])   # equal slices, and ragged slices (padded gather)
+def test_gather_observations_world2_gloo(total):
+    world, row = 2, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, row, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, shape in res:
+        assert ok, f"rank {rank}: gathered rows are not in global env order"
+        assert shape == (total, row)
+
+
+def test_single_process_gather_is_identity():
+    x = torch.randn(5, 7)
+    assert igdist.gather_observations(x) is x

@@ -70,3 +70,26 @@ def test_force_shift_moves_peg_towards_camera(model):
     d0 = np.linalg.norm(M0[:, 3])
     d1 = np.linalg.norm(M1[:, 3])
     assert abs((d0 - d1) - 0.01) < 1e-5
+
+
+def test_oracle_reproduces_golden_fixture(model, golden_dir):
+    """tests/golden/tactile_golden.npz (tools/make_golden_tactile.py): pins the oracle — real cv2 /
+    scipy stages and this repo's raster statement — against drift; a sample of frames keeps it quick."""
+    from oracle import tactile as ot
+    g = np.load(os.path.join(golden_dir, "tactile_golden.npz"))
+    assert np.array_equal(model.depth0, g["depth0"]) and np.array_equal(model.bg_sim, g["bg_sim"])
+    obj_tf = ot.xyzquat_to_tf_numpy(np.concatenate([g["plug_pos"], g["plug_quat"]], 1))
+    checked = contact = 0
+    for f in range(0, 3 * int(g["n_envs"]), 4):
+        e, n = divmod(f, 3)
+        h = ot.OracleAllSight(model, int(g["mesh_id"][e]), int(g["bg_id"][e, n]))
+        ftf = ot.xyzquat_to_tf_numpy(np.concatenate([g["finger_pos"][e, n], g["finger_quat"][e, n]]))[0]
+        h.update_pose_given_sim_pose(ftf, obj_tf[e])
+        color, gd, raw, kind, M = h.render(obj_tf[e], float(g["force"]), return_raw=True)
+        assert np.array_equal(M, g["M"][f])
+        assert np.array_equal(gd, g["gel_depth"][f])
+        assert np.array_equal(color.astype(np.int16) - h.bg_img.astype(np.int16), g["color_delta"][f])
+        assert np.array_equal(ot.tactile_obs(color, h.bg_img, h.mask), g["obs"][f])
+        checked += 1
+        contact += int((gd != 0).any())
+    assert checked >= 10 and contact >= 5

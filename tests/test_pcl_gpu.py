@@ -126,7 +126,8 @@ def test_fps_pipeline_indices_bit_exact(golden, cam):
         assert np.array_equal(out.cpu().numpy(), want_pts)
 
 
-@pytest.mark.parametrize("n,m", [(1, 4), (2, 5), (37, 16), (400, 400), (513, 64), (5184, 400)])
+@pytest.mark.parametrize("n,m", [(1, 4), (2, 5), (37, 16), (37, 64), (128, 400), (129, 300), (384, 400), (385, 400),
+                                 (400, 400), (513, 64), (1024, 400), (1025, 50), (5184, 400)])
 def test_fps_standalone(built_lib, n, m):
     from isaacgyminsertion_b200.pcl_utils import furthest_point_sample
     rng = np.random.default_rng(n)
