@@ -29,7 +29,7 @@ UNIT = "obs/s"
 TACTILE_BYTES_PER_FRAME = 861312      # SURVEY.md 8d / BASELINE.md 4
 PCL_BYTES_PER_ENV_FPS = 51200
 PCL_BYTES_PER_ENV_REF = 57600
-FILL_BYTES_PER_FRAME = 150528 + 150528 + 200704 + 8192 + 8192   # bg_real in; color, depth, obs out; obs_empty in
+FILL_BYTES_PER_FRAME = 150528 + 200704 + 8192   # color, gel_depth, obs written (bg_real / obs_empty sources are L2-resident)
 
 
 def parse():
@@ -325,6 +325,7 @@ def main():
         w_save, world_save = world, world
         t_tac = timed(lambda i: task.update_tactile(ones, ones), K, 3) / K
         t_geom = timed(stage(1), K, 3) / K
+        t_geomfill = timed(stage(8), K, 3) / K
         t_fill = timed(stage(2), K, 3) / K
         t_contact = timed(stage(4), K, 3) / K
 
@@ -338,6 +339,7 @@ def main():
         t_compact = timed(lambda i: gen.compact(d_depth, d_seg, (2, 3), filter_pts.box), K, 3) / K
         pts, cnt, any_ = gen.compact(d_depth, d_seg, (2, 3), filter_pts.box)
         t_fps = timed(lambda i: gen.sample_fps(pts, cnt, any_, 0, 400, out=task._plug_pts), K, 3) / K
+        t_fps_both = timed(lambda i: gen.sample_fps(pts, cnt, any_, None, 400, out=task._both_pts), K, 3) / K
         frames = 3 * E
         counts = eng.contact_counts()
         peaks = {}
@@ -353,10 +355,12 @@ def main():
         kernels = {
             "tac_fill": {"ms": t_fill, "bytes": FILL_BYTES_PER_FRAME * frames},
             "tac_geom": {"ms": t_geom, "bytes": None},
+            "tac_geom_fused_fill": {"ms": t_geomfill, "bytes": FILL_BYTES_PER_FRAME * frames},
             "tac_contact": {"ms": t_contact, "bytes": None},
             "tactile_pipeline": {"ms": t_tac, "bytes": TACTILE_BYTES_PER_FRAME * frames},
             "pcl_compact": {"ms": t_compact, "bytes": (20736 * 2 + 128 + 96 * 4 + 54 * 4) * E},
             "pcl_fps_plug": {"ms": t_fps, "bytes": None},
+            "pcl_fps_plug_socket": {"ms": t_fps_both, "bytes": None},
             "pcl_pipeline": {"ms": t_pcl, "bytes": (PCL_BYTES_PER_ENV_FPS if args.sampler == "fps"
                                                     else PCL_BYTES_PER_ENV_REF) * E},
         }
@@ -364,7 +368,7 @@ def main():
             if v["bytes"]:
                 v["gbs"] = gbs(v["bytes"], v["ms"])
                 v["frac"] = v["gbs"] / peak
-        dom = max(("tac_fill", "tac_geom", "tac_contact", "pcl_compact", "pcl_fps_plug"), key=lambda k: kernels[k]["ms"])
+        dom = max(("tac_geom_fused_fill", "tac_contact", "pcl_compact", "pcl_fps_plug_socket"), key=lambda k: kernels[k]["ms"])
         # the dominant kernel's algorithmic bytes: fill has its own; geom/contact share the frame budget
         dom_bytes = kernels[dom]["bytes"] or (TACTILE_BYTES_PER_FRAME * frames if dom.startswith("tac") else
                                               PCL_BYTES_PER_ENV_FPS * E)

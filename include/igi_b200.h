@@ -91,6 +91,19 @@ int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const i
             int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts, int64_t out_stride,
             int32_t* out_idx, void* stream);
 
+/* K5B with a size-ordered schedule.  Same results as igi_fps for device-side counts; the tasks
+ * are first counting-sorted by point count (descending) and persistent CTAs pull them longest
+ * first, so the SMs finish together although neighbouring envs' clouds differ several-fold in
+ * size.  One call can cover several classes of igi_pcl_compact's output at once: with
+ * task_stride = cap*3, count_stride = 1 and n_tasks = n_envs*n_classes, task t = env*n_classes
+ * + class and out_pts is (n_envs, n_classes, m, 3) - for the task that is its packed
+ * [plug | socket] cloud row (factory_task_insertion.py:1014-1027), no concatenation pass.
+ *   scratch  (n_tasks + 8) i32 caller-owned: schedule counters + the ordered task list
+ */
+int igi_fps_balanced(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
+                     int64_t count_stride, int n_tasks, int m, float* out_pts, int64_t out_stride,
+                     int32_t* out_idx, int32_t* scratch, void* stream);
+
 /* --------------------------------------------------------------------------
  * (T) allsight tactile renderer
  * -------------------------------------------------------------------------- */
@@ -158,8 +171,9 @@ typedef struct IgiTactileFrames {
   const uint8_t* update;        /* (n_envs) update_freq & update_delay or NULL (all) (task :523) */
   const int32_t* mesh_id;       /* (n_envs) */
   const int32_t* bg_id;         /* (n_envs*S) index into bg_real */
-  int32_t stage_mask;           /* 0 = whole pipeline; else bit0 geometry, bit1 fill, bit2 contact
-                                   (profiling: later stages reuse the scratch of an earlier full run) */
+  int32_t stage_mask;           /* 0 = whole pipeline (= 8|4).  bits: 1 geometry alone, 2 standalone fill,
+                                   4 contact, 8 geometry with the fill fused in (excludes 1 and 2).  Single
+                                   stages exist for profiling: later ones reuse the scratch of an earlier run */
 } IgiTactileFrames;
 
 typedef struct IgiTactileScratch {

@@ -258,12 +258,15 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
                                                         const int32_t* count, const int32_t* any,
                                                         int64_t count_stride, int n_fixed, int n_tasks, int m,
                                                         float* out_pts, int64_t out_stride, int32_t* out_idx,
-                                                        int min_n) {
+                                                        int min_n, const int32_t* sched, const int32_t* order) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ FpsCand s_cand[2][kFpsBlock / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // persistent CTAs stride over the tasks; tasks below min_n belong to fps_warp_kernel
-  for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+  // persistent CTAs stride over the tasks; tasks below min_n belong to fps_warp_kernel / fps_sorted_kernel.
+  // With a schedule (igi_fps_balanced) only the tasks fps_order_kernel listed as big are visited.
+  const int n_iter = sched ? sched[4] : n_tasks;
+  for (int it = blockIdx.x; it < n_iter; it += gridDim.x) {
+    const int task = sched ? order[n_tasks - 1 - it] : it;
     const int n = count ? count[(size_t)task * count_stride] : n_fixed;
     if (n < min_n) continue;
     const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
@@ -436,83 +439,78 @@ __device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy,
   for (int i = j + lane; i < m; i += 32) sel[i] = (unsigned short)old;
 }
 
-__global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float* pts, int64_t task_stride,
-                                                                    const int32_t* count, const int32_t* any,
-                                                                    int64_t count_stride, int n_fixed, int n_tasks,
-                                                                    int m, float* out_pts, int64_t out_stride,
-                                                                    int32_t* out_idx) {
-  // dynamic smem: [3][FW_COOP_MAXN] f32 point planes (a warp task uses its own FW_MAXN... slice of every
-  // plane set, see below), then FW_WARPS x m selected indices (u16)
-  extern __shared__ __align__(16) unsigned char fw_smem[];
-  constexpr int PLANE = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
-  float* s_p = reinterpret_cast<float*>(fw_smem);          // [3][PLANE]
-  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * 3 * PLANE);
-  __shared__ int2 s_cand[2][FW_WARPS];
+struct FpsTaskArgs {
+  const float* pts;
+  int64_t task_stride;
+  const int32_t* count;
+  const int32_t* any;
+  int64_t count_stride;
+  int n_fixed, n_tasks, m;
+  float* out_pts;
+  int64_t out_stride;
+  int32_t* out_idx;
+};
+constexpr int FW_PLANE = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
+
+// A task of FW_MAXN+1 .. FW_COOP_MAXN points, run by all warps of the CTA (one barrier per pick).
+__device__ __forceinline__ void fps_coop_task(const FpsTaskArgs& a, int task, int n, float* s_p, int2 (*s_cand)[FW_WARPS]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // ---- long tasks of this CTA's group: all warps together, one after the other
-  for (int t = 0; t < FW_WARPS; ++t) {
-    const int task = blockIdx.x * FW_WARPS + t;
-    if (task >= n_tasks) break;
-    const int n = count ? count[(size_t)task * count_stride] : n_fixed;
-    if (n <= FW_MAXN || n > FW_COOP_MAXN) continue;
-    if (any && any[(size_t)task * count_stride] == 0) continue;   // written as zeros by its warp below
-    float* sx = s_p;
-    float* sy = sx + PLANE;
-    float* sz = sy + PLANE;
-    __syncthreads();
-    const float* src = pts + (size_t)task * task_stride;
-    for (int i = tid; i < 3 * n; i += FW_WARPS * 32) {
-      const int k = i / 3, c = i - 3 * k;
-      s_p[c * PLANE + k] = src[i];
-    }
-    for (int k = n + tid; k < FW_COOP_MAXN; k += FW_WARPS * 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
-    __syncthreads();
-    float temp[FW_COOP_PPL];
-    uint32_t lokey[FW_COOP_PPL];
-    fps_init_state<FW_COOP_PPL>(sx, sy, sz, n, tid, FW_WARPS * 32, temp, lokey);
-    float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
-    int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
-    int old = 0;
-    if (tid == 0) {
-      if (idst) idst[0] = 0;
-      if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
-    }
-    int j = 1;
-    for (; j < m; ++j) {
-      const float best = fps_update<FW_COOP_PPL>(sx, sy, sz, old, tid, FW_WARPS * 32, temp);
-      const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));
-      const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<FW_COOP_PPL>(temp, lokey, wb));
-      if (lane == 0) s_cand[j & 1][warp] = make_int2(wb, (int)wlo);
-      __syncthreads();
-      int fb = -2;
-      uint32_t flo = 0u;
-#pragma unroll
-      for (int w = 0; w < FW_WARPS; ++w) {
-        const int2 c = s_cand[j & 1][w];
-        if (c.x > fb || (c.x == fb && (uint32_t)c.y > flo)) { fb = c.x; flo = (uint32_t)c.y; }
-      }
-      old = (fb < 0) ? 0 : (int)((~flo) & 0xffffu);
-      if (tid == 0) {
-        if (idst) idst[j] = old;
-        if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
-      }
-      if (fb <= 0) { ++j; break; }
-    }
-    for (int i = j + tid; i < m; i += FW_WARPS * 32) {
-      if (idst) idst[i] = old;
-      if (dst) { dst[i * 3 + 0] = sx[old]; dst[i * 3 + 1] = sy[old]; dst[i * 3 + 2] = sz[old]; }
-    }
-  }
+  const int m = a.m;
+  float* sx = s_p;
+  float* sy = sx + FW_PLANE;
+  float* sz = sy + FW_PLANE;
   __syncthreads();
+  const float* src = a.pts + (size_t)task * a.task_stride;
+  for (int i = tid; i < 3 * n; i += FW_WARPS * 32) {
+    const int k = i / 3, c = i - 3 * k;
+    s_p[c * FW_PLANE + k] = src[i];
+  }
+  for (int k = n + tid; k < FW_COOP_MAXN; k += FW_WARPS * 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
+  __syncthreads();
+  float temp[FW_COOP_PPL];
+  uint32_t lokey[FW_COOP_PPL];
+  fps_init_state<FW_COOP_PPL>(sx, sy, sz, n, tid, FW_WARPS * 32, temp, lokey);
+  float* dst = a.out_pts ? a.out_pts + (size_t)task * a.out_stride : nullptr;
+  int32_t* idst = a.out_idx ? a.out_idx + (size_t)task * m : nullptr;
+  int old = 0;
+  if (tid == 0) {
+    if (idst) idst[0] = 0;
+    if (dst) { dst[0] = sx[0]; dst[1] = sy[0]; dst[2] = sz[0]; }
+  }
+  int j = 1;
+  for (; j < m; ++j) {
+    const float best = fps_update<FW_COOP_PPL>(sx, sy, sz, old, tid, FW_WARPS * 32, temp);
+    const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<FW_COOP_PPL>(temp, lokey, wb));
+    if (lane == 0) s_cand[j & 1][warp] = make_int2(wb, (int)wlo);
+    __syncthreads();
+    int fb = -2;
+    uint32_t flo = 0u;
+#pragma unroll
+    for (int w = 0; w < FW_WARPS; ++w) {
+      const int2 c = s_cand[j & 1][w];
+      if (c.x > fb || (c.x == fb && (uint32_t)c.y > flo)) { fb = c.x; flo = (uint32_t)c.y; }
+    }
+    old = (fb < 0) ? 0 : (int)((~flo) & 0xffffu);
+    if (tid == 0) {
+      if (idst) idst[j] = old;
+      if (dst) { dst[j * 3 + 0] = sx[old]; dst[j * 3 + 1] = sy[old]; dst[j * 3 + 2] = sz[old]; }
+    }
+    if (fb <= 0) { ++j; break; }
+  }
+  for (int i = j + tid; i < m; i += FW_WARPS * 32) {
+    if (idst) idst[i] = old;
+    if (dst) { dst[i * 3 + 0] = sx[old]; dst[i * 3 + 1] = sy[old]; dst[i * 3 + 2] = sz[old]; }
+  }
+}
 
-  // ---- one task per warp
-  const int task = blockIdx.x * FW_WARPS + warp;
-  if (task >= n_tasks) return;
-  const int n = count ? count[(size_t)task * count_stride] : n_fixed;
-  const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
-  float* dst = out_pts ? out_pts + (size_t)task * out_stride : nullptr;
-  int32_t* idst = out_idx ? out_idx + (size_t)task * m : nullptr;
+// A task of up to FW_MAXN points (or a dead one: zeros) run by the calling warp in its own plane slice.
+__device__ __forceinline__ void fps_warp_task(const FpsTaskArgs& a, int task, int n, bool live, float* s_p,
+                                              unsigned short* s_sel_all) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int m = a.m;
+  float* dst = a.out_pts ? a.out_pts + (size_t)task * a.out_stride : nullptr;
+  int32_t* idst = a.out_idx ? a.out_idx + (size_t)task * m : nullptr;
   if (!live) {
     for (int i = lane; i < m; i += 32) {
       if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
@@ -520,17 +518,19 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float*
     }
     return;
   }
-  if (n > FW_MAXN) return;  // done above, or fps_kernel's
+  if (n > FW_MAXN) return;  // a cooperative task, or fps_kernel's
   float* sx = s_p + (size_t)warp * FW_MAXN;
-  float* sy = sx + PLANE;
-  float* sz = sy + PLANE;
+  float* sy = sx + FW_PLANE;
+  float* sz = sy + FW_PLANE;
   unsigned short* sel = s_sel_all + warp * m;
-  const float* src = pts + (size_t)task * task_stride;
+  const float* src = a.pts + (size_t)task * a.task_stride;
+  __syncwarp();
   for (int i = lane; i < 3 * n; i += 32) {
     const int k = i / 3, c = i - 3 * k;
-    sx[c * PLANE + k] = src[i];
+    sx[c * FW_PLANE + k] = src[i];
   }
-  for (int k = n + lane; k < FW_MAXN; k += 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
+  const int npad = n <= 128 ? 128 : (n <= 256 ? 256 : FW_MAXN);
+  for (int k = n + lane; k < npad; k += 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
   __syncwarp();
   if (n <= 128) fps_warp_picks<4>(sx, sy, sz, n, m, lane, sel);
   else if (n <= 256) fps_warp_picks<8>(sx, sy, sz, n, m, lane, sel);
@@ -540,6 +540,108 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(const float*
     const int k = sel[i];
     if (idst) idst[i] = k;
     if (dst) { dst[i * 3 + 0] = sx[k]; dst[i * 3 + 1] = sy[k]; dst[i * 3 + 2] = sz[k]; }
+  }
+}
+
+// Static assignment: CTA b owns tasks 4b .. 4b+3 (igi_fps: no scratch for a schedule).
+__global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(FpsTaskArgs a) {
+  // dynamic smem: [3][FW_PLANE] f32 point planes (a warp task uses its own FW_MAXN slice of every plane),
+  // then FW_WARPS x m selected indices (u16)
+  extern __shared__ __align__(16) unsigned char fw_smem[];
+  float* s_p = reinterpret_cast<float*>(fw_smem);
+  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * 3 * FW_PLANE);
+  __shared__ int2 s_cand[2][FW_WARPS];
+  const int warp = threadIdx.x >> 5;
+  // long tasks of this CTA's group: all warps together, one after the other
+  for (int t = 0; t < FW_WARPS; ++t) {
+    const int task = blockIdx.x * FW_WARPS + t;
+    if (task >= a.n_tasks) break;
+    const int n = a.count ? a.count[(size_t)task * a.count_stride] : a.n_fixed;
+    if (n <= FW_MAXN || n > FW_COOP_MAXN) continue;
+    if (a.any && a.any[(size_t)task * a.count_stride] == 0) continue;   // written as zeros by its warp below
+    fps_coop_task(a, task, n, s_p, s_cand);
+  }
+  __syncthreads();
+  const int task = blockIdx.x * FW_WARPS + warp;
+  if (task >= a.n_tasks) return;
+  const int n = a.count ? a.count[(size_t)task * a.count_stride] : a.n_fixed;
+  const bool live = (a.any ? a.any[(size_t)task * a.count_stride] != 0 : true) && n > 0;
+  fps_warp_task(a, task, n, live, s_p, s_sel_all);
+}
+
+// ---- size-ordered schedule (igi_fps_balanced) ---------------------------------------------------------
+// The cost of a task grows with the square of its point count (n picks before the early exit x n/32
+// points per lane), and the counts of neighbouring envs differ by up to 6x, so a static assignment
+// leaves most SMs waiting for the few that drew long tasks.  fps_order_kernel counting-sorts the task
+// ids by descending point count (64 buckets of 16 points; order inside a bucket is whatever the atomics
+// give - it only affects the schedule, never a result); fps_sorted_kernel's persistent CTAs then pull
+// from that list, longest first: whole CTAs for the cooperative sizes, then single warps.
+// sched: [0] n_coop  [1] n_listed  [2] cooperative cursor  [3] warp cursor  [4] n_big (> FW_COOP_MAXN)
+constexpr int FO_BUCKETS = FW_COOP_MAXN / 16;        // 64
+constexpr int FO_COOP_FIRST = FW_MAXN / 16;          // 24: buckets >= this are cooperative sizes
+static_assert(FW_MAXN % 16 == 0 && FW_COOP_MAXN % 16 == 0, "bucket edges must match the size classes");
+
+__global__ void __launch_bounds__(1024) fps_order_kernel(const int32_t* count, const int32_t* any, int64_t count_stride,
+                                                         int n_tasks, int32_t* sched, int32_t* order) {
+  __shared__ int s_hist[FO_BUCKETS + 1], s_base[FO_BUCKETS + 1];
+  const int tid = threadIdx.x;
+  if (tid <= FO_BUCKETS) s_hist[tid] = 0;
+  __syncthreads();
+  auto bucket_of = [&](int task) {
+    const int n = count[(size_t)task * count_stride];
+    const bool live = (any ? any[(size_t)task * count_stride] != 0 : true) && n > 0;
+    if (!live) return 0;
+    if (n > FW_COOP_MAXN) return FO_BUCKETS;
+    return (n - 1) >> 4;
+  };
+  for (int t = tid; t < n_tasks; t += 1024) atomicAdd(&s_hist[bucket_of(t)], 1);
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0, n_coop = 0;
+    for (int b = FO_BUCKETS - 1; b >= 0; --b) {
+      s_base[b] = run;
+      run += s_hist[b];
+      if (b == FO_COOP_FIRST) n_coop = run;
+    }
+    sched[0] = n_coop; sched[1] = run; sched[2] = 0; sched[3] = 0; sched[4] = s_hist[FO_BUCKETS];
+    s_base[FO_BUCKETS] = 0;
+  }
+  __syncthreads();
+  if (tid <= FO_BUCKETS) s_hist[tid] = 0;
+  __syncthreads();
+  for (int t = tid; t < n_tasks; t += 1024) {
+    const int b = bucket_of(t);
+    const int pos = s_base[b] + atomicAdd(&s_hist[b], 1);
+    order[b == FO_BUCKETS ? n_tasks - 1 - pos : pos] = t;   // the big ones are listed from the back
+  }
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_sorted_kernel(FpsTaskArgs a, int32_t* sched, const int32_t* order) {
+  extern __shared__ __align__(16) unsigned char fw_smem[];
+  float* s_p = reinterpret_cast<float*>(fw_smem);
+  unsigned short* s_sel_all = reinterpret_cast<unsigned short*>(fw_smem + sizeof(float) * 3 * FW_PLANE);
+  __shared__ int2 s_cand[2][FW_WARPS];
+  __shared__ int s_item;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_coop = sched[0], n_listed = sched[1];
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(&sched[2], 1);
+    __syncthreads();
+    const int i = s_item;
+    if (i >= n_coop) break;
+    const int task = order[i];
+    fps_coop_task(a, task, a.count[(size_t)task * a.count_stride], s_p, s_cand);
+  }
+  for (;;) {
+    int i = 0;
+    if (lane == 0) i = n_coop + atomicAdd(&sched[3], 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_listed) break;
+    const int task = order[i];
+    const int n = a.count[(size_t)task * a.count_stride];
+    const bool live = (a.any ? a.any[(size_t)task * a.count_stride] != 0 : true) && n > 0;
+    fps_warp_task(a, task, n, live, s_p, s_sel_all);
   }
 }
 
@@ -597,6 +699,37 @@ extern "C" int igi_pcl_sample_gather(const float* pts, const int32_t* count, con
   return IGI_OK;
 }
 
+static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const int32_t* sched, const int32_t* order,
+                            cudaStream_t st) {
+  // worst-case dynamic smem: nmax points (count is on the device)
+  const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
+  IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
+  const int grid = a.n_tasks < sms * per_sm ? a.n_tasks : sms * per_sm;
+  fps_kernel<<<grid, kFpsBlock, smem, st>>>(a.pts, a.task_stride, a.count, a.any, a.count_stride, a.n_fixed, a.n_tasks,
+                                            a.m, a.out_pts, a.out_stride, a.out_idx, min_n, sched, order);
+  IGI_CHECK_LAUNCH("fps_kernel");
+  return IGI_OK;
+}
+
+static int fps_warp_attr() {
+  static bool done = false;
+  if (!done) {
+    IGI_CUDA(cudaFuncSetAttribute(fps_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+    IGI_CUDA(cudaFuncSetAttribute(fps_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+    done = true;
+  }
+  return IGI_OK;
+}
+
 extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
                        int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts,
                        int64_t out_stride, int32_t* out_idx, void* stream) {
@@ -608,38 +741,45 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nmax = count ? task_stride / 3 : n_fixed;
   IGI_REQUIRE(nmax <= 0xffff, "igi_fps: at most 65535 points per task");
-  constexpr int kPlane = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
-  const size_t warp_smem = sizeof(float) * 3 * kPlane + (size_t)FW_WARPS * m * 2;
+  FpsTaskArgs a{pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m, out_pts, out_stride, out_idx};
+  const size_t warp_smem = sizeof(float) * 3 * FW_PLANE + (size_t)FW_WARPS * m * 2;
   const bool warp_ok = warp_smem <= 28 * 1024;  // keeps 8 CTAs (32 task warps) per SM
   const bool need_block = !warp_ok || nmax > FW_COOP_MAXN;
   const bool need_warp = warp_ok && (count != nullptr || n_fixed <= FW_COOP_MAXN);
   if (need_warp) {
-    static bool warp_attr = false;
-    if (!warp_attr) {
-      IGI_CUDA(cudaFuncSetAttribute(fps_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
-      warp_attr = true;
-    }
-    fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, warp_smem, st>>>(
-        pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m, out_pts, out_stride, out_idx);
+    if (int rc = fps_warp_attr()) return rc;
+    fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, warp_smem, st>>>(a);
     IGI_CHECK_LAUNCH("fps_warp_kernel");
   }
-  if (need_block) {
-    // worst-case dynamic smem: task_stride/3 points (count is on the device)
-    const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
-    IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
-    const int grid = n_tasks < sms * per_sm ? n_tasks : sms * per_sm;
-    fps_kernel<<<grid, kFpsBlock, smem, st>>>(pts, task_stride, count, any, count_stride, n_fixed, n_tasks, m,
-                                              out_pts, out_stride, out_idx, need_warp ? FW_COOP_MAXN + 1 : 0);
-    IGI_CHECK_LAUNCH("fps_kernel");
-  }
+  if (need_block) return fps_block_launch(a, nmax, need_warp ? FW_COOP_MAXN + 1 : 0, nullptr, nullptr, st);
+  return IGI_OK;
+}
+
+extern "C" int igi_fps_balanced(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
+                                int64_t count_stride, int n_tasks, int m, float* out_pts, int64_t out_stride,
+                                int32_t* out_idx, int32_t* scratch, void* stream) {
+  IGI_REQUIRE(pts && count && scratch && (out_pts || out_idx), "igi_fps_balanced: null pointer");
+  IGI_REQUIRE(n_tasks >= 0 && m > 0, "igi_fps_balanced: bad dims");
+  IGI_REQUIRE(!out_pts || out_stride >= (int64_t)m * 3, "igi_fps_balanced: out_stride < 3*m");
+  if (n_tasks == 0) return IGI_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nmax = task_stride / 3;
+  IGI_REQUIRE(nmax <= 0xffff, "igi_fps_balanced: at most 65535 points per task");
+  const size_t warp_smem = sizeof(float) * 3 * FW_PLANE + (size_t)FW_WARPS * m * 2;
+  if (warp_smem > 28 * 1024)   // m too large for the resident kernel: the static path handles it
+    return igi_fps(pts, task_stride, count, any, count_stride, 0, n_tasks, m, out_pts, out_stride, out_idx, stream);
+  FpsTaskArgs a{pts, task_stride, count, any, count_stride, 0, n_tasks, m, out_pts, out_stride, out_idx};
+  int32_t* sched = scratch;
+  int32_t* order = scratch + 8;
+  fps_order_kernel<<<1, 1024, 0, st>>>(count, any, count_stride, n_tasks, sched, order);
+  IGI_CHECK_LAUNCH("fps_order_kernel");
+  if (int rc = fps_warp_attr()) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int want = (n_tasks + FW_WARPS - 1) / FW_WARPS;
+  fps_sorted_kernel<<<want < sms * 8 ? want : sms * 8, FW_WARPS * 32, warp_smem, st>>>(a, sched, order);
+  IGI_CHECK_LAUNCH("fps_sorted_kernel");
+  if (nmax > FW_COOP_MAXN) return fps_block_launch(a, nmax, FW_COOP_MAXN + 1, sched, order, st);
   return IGI_OK;
 }

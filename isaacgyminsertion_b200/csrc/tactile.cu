@@ -291,6 +291,54 @@ __global__ void tac_gel_shade(const float* __restrict__ gel_tris, const unsigned
   shade(p, n, bg_sim + 3 * i);
 }
 
+// ---- K2f: fill -----------------------------------------------------------------------------
+struct FillArgs {
+  const uint8_t* bg_real;    // (n_bg, TH, TW, 3)
+  const int32_t* bg_id;      // (F) index into bg_real
+  const float* obs_empty;    // (OBS_H*OBS_W)
+  const int32_t* counts;     // (F) -1 => frame not updated
+  uint8_t* color;            // (F, TH, TW, 3) or null
+  float* gel_depth;          // (F, TH, TW) or null
+  float* obs;                // frame (e,n) at obs + e*obs_env_stride + n*obs_sensor_stride
+  int64_t obs_env_stride, obs_sensor_stride;
+  int sensors_per_env;
+  int n_frames;
+};
+constexpr int FILL_BLOCK = 256;
+constexpr int FILL_PARTS = 4;  // CTAs per frame
+
+// The no-contact result of frame f (exact: diff = 0 => colour = bg_real, gel_depth = 0, obs = obs_empty),
+// written with 128-bit streaming stores by threads [first, first + stride, ...).
+__device__ __forceinline__ void fill_frame(const FillArgs& a, int f, int first, int stride) {
+  if (a.color) {
+    constexpr int NV = TW * TH * 3 / 16;  // 9408 uint4
+    const uint4* src = reinterpret_cast<const uint4*>(a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3);
+    uint4* dst = reinterpret_cast<uint4*>(a.color + (size_t)f * TW * TH * 3);
+#pragma unroll 4
+    for (int i = first; i < NV; i += stride) __stcs(dst + i, __ldg(src + i));
+  }
+  if (a.gel_depth) {
+    constexpr int NV = TW * TH * 4 / 16;  // 12544 uint4
+    uint4* dst = reinterpret_cast<uint4*>(a.gel_depth + (size_t)f * TW * TH);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+    for (int i = first; i < NV; i += stride) __stcs(dst + i, z);
+  }
+  {
+    constexpr int NV = OBS_W * OBS_H * 4 / 16;  // 512 float4
+    const float4* src = reinterpret_cast<const float4*>(a.obs_empty);
+    float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
+                                            (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride);
+    for (int i = first; i < NV; i += stride) dst[i] = __ldg(src + i);
+  }
+}
+
+__global__ void __launch_bounds__(FILL_BLOCK) tac_fill(FillArgs a) {
+  const int f = blockIdx.x / FILL_PARTS, part = blockIdx.x % FILL_PARTS;
+  if (a.counts[f] < 0) return;
+  fill_frame(a, f, part * FILL_BLOCK + threadIdx.x, FILL_PARTS * FILL_BLOCK);
+}
+
 // ---- K1a: geometry ----------------------------------------------------------------------
 struct MeshInfo { int face_off, n_faces, cl_off, n_cl; };
 struct Cluster { float cx, cy, cz, r; int first, count, pad0, pad1; };
@@ -320,6 +368,8 @@ struct GeomArgs {
   int32_t* overflow;         // (1)
   int sensors_per_env, kmax;
   float force_const;
+  int fused_fill;            // 1: this kernel also writes the frame's no-contact result (fill)
+  FillArgs fill;
 };
 
 __device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid, float x, float y, float z) {
@@ -396,6 +446,10 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     return;
   }
   for (int i = tid; i < TW; i += GEOM_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
+  // Fused fill: warps 1.. stream the frame's no-contact result out while lane 0 of warp 0 runs the serial
+  // f64 pose chain; the stores drain in the background of the culling work below.  tac_contact, the next
+  // kernel on the stream, rewrites the dirty window.
+  if (a.fused_fill && warp > 0) fill_frame(a.fill, f, tid - 32, GEOM_BLOCK - 32);
   if (tid == 0) {
     // ---- pose chain in f64 (xyzquat_to_tf_numpy, update_camera_pose_from_matrix, adjust_with_force)
     double q[4], R[9], Ro[9];
@@ -553,47 +607,6 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
       a.bbox[4 * f + 2] = s_bb[2]; a.bbox[4 * f + 3] = s_bb[3];
       a.worklist[atomicAdd(a.work_n, 1)] = f;
     }
-  }
-}
-
-// ---- K2f: fill -----------------------------------------------------------------------------
-struct FillArgs {
-  const uint8_t* bg_real;    // (n_bg, TH, TW, 3)
-  const int32_t* bg_id;      // (F) index into bg_real
-  const float* obs_empty;    // (OBS_H*OBS_W)
-  const int32_t* counts;     // (F) -1 => frame not updated
-  uint8_t* color;            // (F, TH, TW, 3) or null
-  float* gel_depth;          // (F, TH, TW) or null
-  float* obs;                // frame (e,n) at obs + e*obs_env_stride + n*obs_sensor_stride
-  int64_t obs_env_stride, obs_sensor_stride;
-  int sensors_per_env;
-  int n_frames;
-};
-constexpr int FILL_BLOCK = 256;
-constexpr int FILL_PARTS = 4;  // CTAs per frame
-
-__global__ void __launch_bounds__(FILL_BLOCK) tac_fill(FillArgs a) {
-  const int f = blockIdx.x / FILL_PARTS, part = blockIdx.x % FILL_PARTS;
-  if (a.counts[f] < 0) return;
-  const int tid = threadIdx.x;
-  if (a.color) {
-    constexpr int NV = TW * TH * 3 / 16;  // 9408 uint4
-    const uint4* src = reinterpret_cast<const uint4*>(a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3);
-    uint4* dst = reinterpret_cast<uint4*>(a.color + (size_t)f * TW * TH * 3);
-    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) __stcs(dst + i, __ldg(src + i));
-  }
-  if (a.gel_depth) {
-    constexpr int NV = TW * TH * 4 / 16;  // 12544 uint4
-    uint4* dst = reinterpret_cast<uint4*>(a.gel_depth + (size_t)f * TW * TH);
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) __stcs(dst + i, z);
-  }
-  {
-    constexpr int NV = OBS_W * OBS_H * 4 / 16;  // 512 float4
-    const float4* src = reinterpret_cast<const float4*>(a.obs_empty);
-    float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
-                                            (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride);
-    for (int i = part * FILL_BLOCK + tid; i < NV; i += FILL_PARTS * FILL_BLOCK) dst[i] = __ldg(src + i);
   }
 }
 
@@ -1292,10 +1305,20 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   const int F = fr->n_envs * fr->sensors_per_env;
   if (F == 0) return IGI_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int stages = fr->stage_mask ? fr->stage_mask : 7;
+  // stage bits: 1 geometry alone, 2 standalone fill, 4 contact, 8 geometry with the fill fused in
+  // (the product path: 0 = 8 | 4).  1/2 exist for per-stage timing and for callers that want one stage.
+  const int stages = fr->stage_mask ? fr->stage_mask : (8 | 4);
+  IGI_REQUIRE((stages & ~15) == 0 && !((stages & 8) && (stages & 3)),
+              "igi_tactile_render: stage_mask 8 (fused geometry+fill) excludes bits 1 and 2");
   // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
-  if (stages & 1) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
+  if (stages & 9) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
   else IGI_CUDA(cudaMemsetAsync(sc->counters + 1, 0, sizeof(int32_t), s));
+  FillArgs fa{};
+  fa.bg_real = st->bg_real; fa.bg_id = fr->bg_id; fa.obs_empty = st->obs_empty; fa.counts = sc->counts;
+  fa.color = out->color; fa.gel_depth = out->gel_depth; fa.obs = out->obs;
+  fa.obs_env_stride = out->obs_env_stride; fa.obs_sensor_stride = out->obs_sensor_stride;
+  fa.sensors_per_env = fr->sensors_per_env;
+  fa.n_frames = F;
   GeomArgs g{};
   g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
@@ -1304,16 +1327,12 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
-  if (stages & 1) {
+  g.fused_fill = (stages & 8) ? 1 : 0;
+  g.fill = fa;
+  if (stages & 9) {
     tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
     IGI_CHECK_LAUNCH("tac_geom");
   }
-  FillArgs fa{};
-  fa.bg_real = st->bg_real; fa.bg_id = fr->bg_id; fa.obs_empty = st->obs_empty; fa.counts = sc->counts;
-  fa.color = out->color; fa.gel_depth = out->gel_depth; fa.obs = out->obs;
-  fa.obs_env_stride = out->obs_env_stride; fa.obs_sensor_stride = out->obs_sensor_stride;
-  fa.sensors_per_env = fr->sensors_per_env;
-  fa.n_frames = F;
   if (stages & 2) {
     tac_fill<<<F * FILL_PARTS, FILL_BLOCK, 0, s>>>(fa);
     IGI_CHECK_LAUNCH("tac_fill");

@@ -228,6 +228,36 @@ class BatchedPointCloud:
     # -- K5B ---------------------------------------------------------------------
     @torch.no_grad()
     def sample_fps(self, pts, cnt, any_, cls, m, out=None, return_idx=False):
+        """FPS of class `cls` (int) or of every class at once (cls=None: out is (n, C, m, 3)).
+        Size-ordered schedule (igi_fps_balanced)."""
+        n, C, cap, _ = pts.shape
+        if cls is None:
+            shape, n_tasks = (n, C, m, 3), n * C
+            p0, c0, a0 = pts, cnt, any_
+            task_stride, count_stride = pts.stride(1), 1
+        else:
+            shape, n_tasks = (n, m, 3), n
+            p0, c0, a0 = pts[:, cls], cnt[:, cls], any_[:, cls]
+            task_stride, count_stride = pts.stride(0), C
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        assert tuple(out.shape) == shape and out.stride(-1) == 1 and out.stride(-2) == 3
+        out_stride = out.stride(-3)
+        if cls is None:
+            assert out.stride(0) == C * out_stride, "all-class output must be dense over (env, class)"
+        idx = torch.empty(shape[:-1], dtype=torch.int32, device=self.device) if return_idx else None
+        scratch = self._buf("fps_sched", (n_tasks + 8,), torch.int32)
+        rc = self.lib.igi_fps_balanced(
+            _c.c_void_p(p0.data_ptr()), _c.c_int64(task_stride),
+            _c.c_void_p(c0.data_ptr()), _c.c_void_p(a0.data_ptr()), _c.c_int64(count_stride),
+            _c.c_int(n_tasks), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out_stride),
+            _lib.dptr(idx), _lib.dptr(scratch), _lib.stream_ptr(self.device))
+        _lib.check(rc, "igi_fps_balanced")
+        return (out, idx) if return_idx else out
+
+    @torch.no_grad()
+    def sample_fps_static(self, pts, cnt, any_, cls, m, out=None, return_idx=False):
+        """igi_fps: same results, static task assignment (no scratch)."""
         n, C, cap, _ = pts.shape
         if out is None:
             out = torch.empty((n, m, 3), dtype=torch.float32, device=self.device)

@@ -69,7 +69,12 @@ class FactoryTaskInsertionTactileObs:
         self.pcl = self.obs_packed[:, TACTILE_FLOATS:]
         self.tactile_queue = torch.zeros((N, tact_hist_len, 3, OBS_LEN), dtype=torch.float32, device=dev)
         self.pcl_queue = torch.zeros((N, pcl_hist_len, self.pcl_floats), dtype=torch.float32, device=dev)
-        self.socket_pcl = torch.zeros((N, num_points_socket, 3), dtype=torch.float32, device=dev)
+        # plug and socket clouds live side by side, [plug | socket] per env = the layout of the merged pcl
+        # row (:1014-1027), so one all-class FPS launch writes both and no concatenation is needed
+        self._both_pts = (torch.zeros((N, 2, num_points, 3), dtype=torch.float32, device=dev)
+                          if num_points == num_points_socket else None)
+        self.socket_pcl = (self._both_pts[:, 1] if self._both_pts is not None else
+                           torch.zeros((N, num_points_socket, 3), dtype=torch.float32, device=dev))
         self.got_socket = torch.zeros((N, 1), dtype=torch.int32, device=dev)
         self._socket_pending = True        # host mirror of `not self.got_socket.all()` (no sync)
         self.pcl_pos_noise = torch.randn(N, 1, 3, device=dev)
@@ -87,7 +92,8 @@ class FactoryTaskInsertionTactileObs:
             self.pcl_generator = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props,
                                                   sample_num=num_points, filter_func=filter_pts, pt_in_local=True,
                                                   graphics_device=dev, compute_device=dev, sampler=sampler)
-            self._plug_pts = torch.zeros((N, num_points, 3), dtype=torch.float32, device=dev)
+            self._plug_pts = (self._both_pts[:, 0] if self._both_pts is not None else
+                              torch.zeros((N, num_points, 3), dtype=torch.float32, device=dev))
         # state the reference reads from gym tensors
         z3 = torch.zeros((N, 3), device=dev)
         q4 = torch.tensor([0, 0, 0, 1.0], device=dev).repeat(N, 1)
@@ -147,14 +153,19 @@ class FactoryTaskInsertionTactileObs:
         box = filter_pts.box
         compute_socket = self._socket_pending
         pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3) if compute_socket else (2,), box)     # :956-959,975
-        self._sample(pts, cnt, any_, 0, self.num_points, self._plug_pts)                             # :961-964
+        fused = compute_socket and self.sampler == "fps" and self._both_pts is not None
+        if fused:    # plug and socket tasks in one size-ordered launch
+            gen.engine.sample_fps(pts, cnt, any_, None, self.num_points, out=self._both_pts)
+        else:
+            self._sample(pts, cnt, any_, 0, self.num_points, self._plug_pts)                         # :961-964
         plug_pts = self._plug_pts
         noisy = pcl_noise.clone()
         if self.pcl_noise_enabled:
             plug_pts = torch.where(noisy[:, None, None], self.pcl_process.augment(
                 plug_pts, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), plug_pts)          # :966-969
         if compute_socket:                                                                          # :972-989
-            self._sample(pts, cnt, any_, 1, self.num_points_socket, self.socket_pcl)
+            if not fused:
+                self._sample(pts, cnt, any_, 1, self.num_points_socket, self.socket_pcl)
             restarted = self.got_socket[:, 0] == 0
             noisy = noisy | restarted
             if self.pcl_noise_enabled:
@@ -163,7 +174,10 @@ class FactoryTaskInsertionTactileObs:
             self.got_socket[restarted] = 1
             update = update | restarted
             self._socket_pending = False
-        merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)                  # :1014-1027
+        if plug_pts is self._plug_pts and self._both_pts is not None:
+            merged = self._both_pts.view(N, -1)                                                      # :1014-1027
+        else:
+            merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)
         self.pcl.copy_(torch.where(update[:, None], merged, self.pcl))
         self.pcl_queue[:, 1:] = self.pcl_queue[:, :-1].clone().detach()                              # :1046-1048
         self.pcl_queue[:, 0, ...] = self.pcl

@@ -124,6 +124,55 @@ def test_fps_pipeline_indices_bit_exact(golden, cam):
         want_pts, want_idx = ofps.fps_batch(lst, 400)
         assert np.array_equal(idx.cpu().numpy(), want_idx)
         assert np.array_equal(out.cpu().numpy(), want_pts)
+        # the static-assignment entry point (igi_fps) gives the same result
+        out_s, idx_s = gen.engine.sample_fps_static(pts, cnt, any_, cls, 400, return_idx=True)
+        assert torch.equal(idx_s, idx) and torch.equal(out_s, out)
+    # every class in one size-ordered launch: (n, C, m, 3), the packed [plug | socket] layout
+    both, idx_b = gen.engine.sample_fps(pts, cnt, any_, None, 400, return_idx=True)
+    for cls in (0, 1):
+        out, idx = gen.engine.sample_fps(pts, cnt, any_, cls, 400, return_idx=True)
+        assert torch.equal(both[:, cls], out) and torch.equal(idx_b[:, cls], idx)
+
+
+def test_fps_balanced_mixed_sizes(built_lib):
+    """Size-ordered schedule over tasks of every size class (dead, warp-resident, cooperative, block
+    kernel), interleaved so that the ordered list differs from the task order."""
+    import ctypes as c
+    from isaacgyminsertion_b200 import _lib
+    lib = _lib.load()
+    sizes = [0, 1, 5, 100, 128, 129, 256, 257, 384, 385, 700, 1024, 1025, 3000, 17, 400, 64, 383, 1023, 2]
+    rng = np.random.default_rng(11)
+    T, cap, m = 3 * len(sizes), 3000, 400
+    counts = np.array([sizes[(7 * t) % len(sizes)] for t in range(T)], dtype=np.int32)
+    anyf = np.ones(T, dtype=np.int32)
+    anyf[5] = 0                                          # a dead task with points
+    pts = (rng.random((T, cap, 3)) * 0.5 + 0.1).astype(np.float32)
+    pts[3, 50:100] = pts[3, 0:50]                        # exact ties
+    d_pts = torch.from_numpy(pts).cuda()
+    d_cnt, d_any = torch.from_numpy(counts).cuda(), torch.from_numpy(anyf).cuda()
+    out = torch.full((T, m, 3), -7.0, device="cuda")
+    idx = torch.full((T, m), -7, dtype=torch.int32, device="cuda")
+    scratch = torch.empty(T + 8, dtype=torch.int32, device="cuda")
+    rc = lib.igi_fps_balanced(_lib.dptr(d_pts), c.c_int64(cap * 3), _lib.dptr(d_cnt), _lib.dptr(d_any), c.c_int64(1),
+                              c.c_int(T), c.c_int(m), _lib.dptr(out), c.c_int64(m * 3), _lib.dptr(idx),
+                              _lib.dptr(scratch), _lib.stream_ptr(d_pts.device))
+    _lib.check(rc, "igi_fps_balanced")
+    sched = scratch[:5].cpu().numpy()
+    live = (counts > 0) & (anyf != 0)
+    assert sched[4] == int(((counts > 1024) & live).sum())
+    assert sched[1] == T - sched[4] and sched[0] == int(((counts > 384) & (counts <= 1024) & live).sum())
+    order = scratch[8:8 + sched[1]].cpu().numpy()
+    assert len(set(order.tolist())) == sched[1]          # every listed task exactly once
+    key = np.where(live, counts, 0)[order]
+    assert np.all(((key[:-1] - 1).clip(0) >> 4) >= ((key[1:] - 1).clip(0) >> 4))   # longest first (16-point buckets)
+    got_idx, got = idx.cpu().numpy(), out.cpu().numpy()
+    for t in range(T):
+        if not live[t]:
+            assert not got_idx[t].any() and not got[t].any(), t
+            continue
+        want = ofps.furthest_point_sample(pts[t, :counts[t]], m)
+        assert np.array_equal(got_idx[t], want), (t, counts[t])
+        assert np.array_equal(got[t], pts[t][want]), t
 
 
 @pytest.mark.parametrize("n,m", [(1, 4), (2, 5), (37, 16), (37, 64), (128, 400), (129, 300), (384, 400), (385, 400),

@@ -272,6 +272,11 @@ def test_edge_cases(built_lib):
     # zero-sized batches are accepted by the C-ABI without a launch
     before = lib.igi_launch_count()
     import ctypes as c
-    rc = lib.igi_fps(_lib.dptr(task._plug_pts), c.c_int64(1200), None, None, c.c_int64(1), c.c_int(400), c.c_int(0),
-                     c.c_int(16), _lib.dptr(task._plug_pts), c.c_int64(1200), None, _lib.stream_ptr(task.device))
+    buf = torch.zeros((n, 400, 3), device=DEV)
+    rc = lib.igi_fps(_lib.dptr(buf), c.c_int64(1200), None, None, c.c_int64(1), c.c_int(400), c.c_int(0),
+                     c.c_int(16), _lib.dptr(buf), c.c_int64(1200), None, _lib.stream_ptr(task.device))
+    assert rc == 0 and lib.igi_launch_count() == before
+    rc = lib.igi_fps_balanced(_lib.dptr(buf), c.c_int64(1200), _lib.dptr(task.got_socket), None, c.c_int64(1), c.c_int(0),
+                              c.c_int(16), _lib.dptr(buf), c.c_int64(1200), None, _lib.dptr(task.got_socket),
+                              _lib.stream_ptr(task.device))
     assert rc == 0 and lib.igi_launch_count() == before
