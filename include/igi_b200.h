@@ -216,6 +216,10 @@ int igi_tactile_render(const IgiTactileMeshes* meshes, const IgiTactileStatic* s
  * hold, so small inputs exercise the multi-region path.  0 restores the built-in budget. */
 int igi_tactile_set_region_budget(int pixels);
 
+/* Tuning hook: which parts of the no-contact result (1 colour, 2 gel_depth, 4 obs) the geometry kernel
+ * writes; the contact kernel writes the others.  Results do not depend on the split. */
+int igi_tactile_set_fill_split(int geom_parts);
+
 /* K3 alone: color (F,H,W,3) u8 -> obs.  Replaces factory_task_insertion.py:546-574. */
 int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,
                     int64_t obs_stride, void* stream);

@@ -73,6 +73,15 @@ __device__ __forceinline__ void igi_bulk_g2s(void* smem_dst, const void* gsrc, u
       "l"(gsrc), "r"(bytes), "r"(igi_smem_u32(bar))
       : "memory");
 }
+// shared -> global bulk copy (asynchronous, bulk-group completion); bytes % 16 == 0, 16-byte aligned.
+__device__ __forceinline__ void igi_bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(igi_smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void igi_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until the bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void igi_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void igi_fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

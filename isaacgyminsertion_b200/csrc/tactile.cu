@@ -74,7 +74,7 @@ __device__ __forceinline__ bool owns_zero(V3 n) {
 __device__ __forceinline__ float edge_fn(float dx, float dy, V3 n) { return sub(add(mul(dx, n.x), mul(dy, n.y)), n.z); }
 __device__ __forceinline__ bool edge_in(float e, V3 n) { return e < 0.0f || (e == 0.0f && owns_zero(n)); }
 
-struct Setup {       // 64 B record
+struct __align__(16) Setup {       // 64 B record
   V3 n0, n1, n2, N;  // edge-plane normals BxC, CxA, AxB and face normal (B-A)x(C-A)
   float det;         // N.A  (< 0: front-facing)
   uint32_t bbox;     // x0 | y0<<8 | x1<<16 | y1<<24 (pixels, inclusive, conservative)
@@ -303,6 +303,7 @@ struct FillArgs {
   int64_t obs_env_stride, obs_sensor_stride;
   int sensors_per_env;
   int n_frames;
+  int parts;                 // bit 0 colour, bit 1 gel_depth, bit 2 obs
 };
 constexpr int FILL_BLOCK = 256;
 constexpr int FILL_PARTS = 4;  // CTAs per frame
@@ -310,21 +311,21 @@ constexpr int FILL_PARTS = 4;  // CTAs per frame
 // The no-contact result of frame f (exact: diff = 0 => colour = bg_real, gel_depth = 0, obs = obs_empty),
 // written with 128-bit streaming stores by threads [first, first + stride, ...).
 __device__ __forceinline__ void fill_frame(const FillArgs& a, int f, int first, int stride) {
-  if (a.color) {
+  if (a.color && (a.parts & 1)) {
     constexpr int NV = TW * TH * 3 / 16;  // 9408 uint4
     const uint4* src = reinterpret_cast<const uint4*>(a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3);
     uint4* dst = reinterpret_cast<uint4*>(a.color + (size_t)f * TW * TH * 3);
 #pragma unroll 4
     for (int i = first; i < NV; i += stride) __stcs(dst + i, __ldg(src + i));
   }
-  if (a.gel_depth) {
+  if (a.gel_depth && (a.parts & 2)) {
     constexpr int NV = TW * TH * 4 / 16;  // 12544 uint4
     uint4* dst = reinterpret_cast<uint4*>(a.gel_depth + (size_t)f * TW * TH);
     const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
     for (int i = first; i < NV; i += stride) __stcs(dst + i, z);
   }
-  {
+  if (a.parts & 4) {
     constexpr int NV = OBS_W * OBS_H * 4 / 16;  // 512 float4
     const float4* src = reinterpret_cast<const float4*>(a.obs_empty);
     float4* dst = reinterpret_cast<float4*>(a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
@@ -368,7 +369,8 @@ struct GeomArgs {
   int32_t* overflow;         // (1)
   int sensors_per_env, kmax;
   float force_const;
-  int fused_fill;            // 1: this kernel also writes the frame's no-contact result (fill)
+  int fused_fill;            // 1: this kernel also writes (fill.parts of) the frame's no-contact result
+  int list_all;              // 1: every live frame goes to the worklist (tac_contact fills the other parts)
   FillArgs fill;
 };
 
@@ -410,33 +412,18 @@ __device__ unsigned long long g_ct_prof[32];
 
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
-constexpr int GEOM_SMALL_BLOCKS = 8;   // triangles touching up to this many 8x8 blocks are tested by their own thread
-constexpr int GEOM_MAX_BIG = 160;      // larger ones are queued (with their setup record) and tested by a whole warp
-
-// Shrinks [x0,x1]x[y0,y1] to the 8x8 image blocks of it in which the triangle may produce a fragment in
-// front of the gel (conservative: edge planes and nearest plane depth against level 3 of the depth0
-// max-pyramid).  `lane`/`nl` split the blocks between cooperating lanes.  Returns false if none.
-__device__ __forceinline__ void blocks_visible(const Setup& s, const float* __restrict__ tdx, const float* __restrict__ tdy,
-                                               const float* __restrict__ hz3, int hw3, int x0, int y0, int x1, int y1,
-                                               int lane, int nl, int& vx0, int& vy0, int& vx1, int& vy1) {
-  const int gbx0 = x0 >> 3, gby0 = y0 >> 3;
-  const int nbx = (x1 >> 3) - gbx0 + 1, nb = nbx * ((y1 >> 3) - gby0 + 1);
-  vx0 = TW; vy0 = TH; vx1 = -1; vy1 = -1;
-  for (int b = lane; b < nb; b += nl) {
-    const int gy = gby0 + b / nbx, gx = gbx0 + b - (b / nbx) * nbx;
-    const int cx0 = max(gx * 8, x0), cx1 = min(gx * 8 + 7, x1), cy0 = max(gy * 8, y0), cy1 = min(gy * 8 + 7, y1);
-    if (block_may_hit(s, tdx, tdy, cx0, cx1, cy0, cy1, hz3[gy * hw3 + gx])) {
-      vx0 = min(vx0, cx0); vy0 = min(vy0, cy0); vx1 = max(vx1, cx1); vy1 = max(vy1, cy1);
-    }
-  }
-}
+constexpr int GEOM_ROUND = 256;        // faces prepared per round (2 per thread); survivors are queued in shared memory
+constexpr int GEOM_WARPS = GEOM_BLOCK / 32;
 
 __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
   __shared__ float sM[12];
   __shared__ int s_cl[GEOM_MAX_CL];
-  __shared__ Setup s_big[GEOM_MAX_BIG];
+  __shared__ __align__(16) Setup s_q[GEOM_ROUND];   // survivors of the cheap culls of this round
+  __shared__ int s_qoff[GEOM_ROUND];                // their 8x8-block counts -> exclusive prefix
+  __shared__ uint32_t s_vmask[GEOM_ROUND][2];       // block columns / rows in which the triangle may be visible
+  __shared__ int s_wsum[GEOM_WARPS];
   __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
-  __shared__ int s_ncl, s_count, s_nbig;
+  __shared__ int s_ncl, s_count, s_nq[2];  // queue length, double-buffered by round parity
   __shared__ int s_bb[4];
   const int f = blockIdx.x;
   const int env = f / a.sensors_per_env;
@@ -491,7 +478,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     }
     s_ncl = 0;
     s_count = 0;
-    s_nbig = 0;
+    s_nq[0] = 0; s_nq[1] = 0;
     s_bb[0] = TW; s_bb[1] = TH; s_bb[2] = -1; s_bb[3] = -1;
   }
   __syncthreads();
@@ -559,43 +546,92 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     return true;
   };
 
-  // ---- faces of the surviving clusters, flattened so that every thread has one (clusters hold <= 64)
-  for (int it = tid; it < ncl * 64; it += GEOM_BLOCK) {
-    const int2 cl = *reinterpret_cast<const int2*>(&a.clusters[s_cl[it >> 6]].first);  // first, count
-    for (int k = it & 63; k < cl.y; k += 64) {  // clusters normally hold <= 64 faces: one pass
+  // ---- faces of the surviving clusters, GEOM_ROUND at a time.  Per round: (1) every thread prepares two
+  // faces (transform, facing, gel distance, screen box, hi-z) and queues the survivors' setup records;
+  // (2) the queued triangles' 8x8 image blocks are flattened into one item list (block scan of the block
+  // counts) so that every thread tests one (triangle, block) pair against the gel whatever the triangle
+  // sizes are; (3) triangles with a block in which they may be visible are emitted with the box of
+  // those blocks.
+  const int n_faces_padded = ncl * 64;
+  for (int r0 = 0, par = 0; r0 < n_faces_padded; r0 += GEOM_ROUND, par ^= 1) {
+    for (int it = r0 + tid; it < min(r0 + GEOM_ROUND, n_faces_padded); it += GEOM_BLOCK) {
+      const int2 cl = *reinterpret_cast<const int2*>(&a.clusters[s_cl[it >> 6]].first);  // first, count
+      const int k = it & 63;
+      if (k >= cl.y) continue;
       const int face = cl.x + k;
       Setup s;
       int x0, y0, x1, y1;
       if (!prepare(face, s, x0, y0, x1, y1)) continue;
-      // visibility against the gel, block by block; triangles over many blocks go to the warp queue
-      const int nb = ((x1 >> 3) - (x0 >> 3) + 1) * ((y1 >> 3) - (y0 >> 3) + 1);
-      if (nb > GEOM_SMALL_BLOCKS) {
-        const int slot = atomicAdd(&s_nbig, 1);
-        if (slot < GEOM_MAX_BIG) {
-          s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
-          s.tri = (uint32_t)face;
-          s_big[slot] = s;
-          continue;
-        }
-      }
-      int vx0, vy0, vx1, vy1;
-      blocks_visible(s, s_dxp, s_dyp, hz3, hw3, x0, y0, x1, y1, 0, 1, vx0, vy0, vx1, vy1);
-      if (vx1 < 0) continue;
-      emit(s, face, vx0, vy0, vx1, vy1);
+      s.bbox = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+      s.tri = (uint32_t)face;
+      const int slot = atomicAdd(&s_nq[par], 1);
+      s_q[slot] = s;
+      s_qoff[slot] = ((x1 >> 3) - (x0 >> 3) + 1) * ((y1 >> 3) - (y0 >> 3) + 1);
+      s_vmask[slot][0] = 0u; s_vmask[slot][1] = 0u;
     }
-  }
-  __syncthreads();
-  // ---- queued large triangles: one warp each, lanes over the 8x8 blocks
-  const int nbig = min(s_nbig, GEOM_MAX_BIG);
-  for (int q = warp; q < nbig; q += GEOM_BLOCK / 32) {
-    Setup s = s_big[q];
-    const int face = (int)s.tri;
-    const int x0 = (int)(s.bbox & 255u), y0 = (int)((s.bbox >> 8) & 255u), x1 = (int)((s.bbox >> 16) & 255u), y1 = (int)(s.bbox >> 24);
-    int vx0, vy0, vx1, vy1;
-    blocks_visible(s, s_dxp, s_dyp, hz3, hw3, x0, y0, x1, y1, lane, 32, vx0, vy0, vx1, vy1);
-    vx0 = __reduce_min_sync(0xffffffffu, vx0); vy0 = __reduce_min_sync(0xffffffffu, vy0);
-    vx1 = __reduce_max_sync(0xffffffffu, vx1); vy1 = __reduce_max_sync(0xffffffffu, vy1);
-    if (lane == 0 && vx1 >= 0) emit(s, face, vx0, vy0, vx1, vy1);
+    __syncthreads();
+    // The counter of the NEXT round is the other one, so a thread that runs ahead cannot disturb this read;
+    // this one is reused two rounds later, after at least one more barrier.
+    const int nq = s_nq[par];
+    if (nq == 0) continue;   // uniform: nothing was queued, the counter is still 0
+    // exclusive scan of the block counts (two queue entries per thread)
+    int total;
+    {
+      const int e0 = 2 * tid, e1 = 2 * tid + 1;
+      const int c0 = e0 < nq ? s_qoff[e0] : 0, c1 = e1 < nq ? s_qoff[e1] : 0;
+      int incl = c0 + c1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0;
+      total = 0;
+#pragma unroll
+      for (int w = 0; w < GEOM_WARPS; ++w) {
+        const int t = s_wsum[w];
+        if (w < warp) woff += t;
+        total += t;
+      }
+      const int base = woff + incl - c0 - c1;
+      if (e0 < nq) s_qoff[e0] = base;
+      if (e1 < nq) s_qoff[e1] = base + c0;
+    }
+    __syncthreads();
+    for (int it = tid; it < total; it += GEOM_BLOCK) {
+      int lo = 0, hi = nq - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_qoff[mid] <= it) lo = mid; else hi = mid - 1;
+      }
+      const Setup& s = s_q[lo];
+      const int b = it - s_qoff[lo];
+      const uint32_t bb = s.bbox;
+      const int x0 = (int)(bb & 255u), y0 = (int)((bb >> 8) & 255u), x1 = (int)((bb >> 16) & 255u), y1 = (int)(bb >> 24);
+      const int gbx0 = x0 >> 3, nbx = (x1 >> 3) - gbx0 + 1;
+      const int by = b / nbx;
+      const int gy = (y0 >> 3) + by, gx = gbx0 + b - by * nbx;
+      const int cx0 = max(gx * 8, x0), cx1 = min(gx * 8 + 7, x1), cy0 = max(gy * 8, y0), cy1 = min(gy * 8 + 7, y1);
+      if (block_may_hit(s, s_dxp, s_dyp, cx0, cx1, cy0, cy1, hz3[gy * hw3 + gx])) {
+        atomicOr(&s_vmask[lo][0], 1u << gx);
+        atomicOr(&s_vmask[lo][1], 1u << gy);
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < nq; q += GEOM_BLOCK) {
+      const uint32_t mx = s_vmask[q][0], my = s_vmask[q][1];
+      if (mx == 0u) continue;
+      Setup s = s_q[q];
+      const uint32_t bb = s.bbox;
+      const int x0 = (int)(bb & 255u), y0 = (int)((bb >> 8) & 255u), x1 = (int)((bb >> 16) & 255u), y1 = (int)(bb >> 24);
+      const int vx0 = max((__ffs(mx) - 1) * 8, x0), vx1 = min((31 - __clz(mx)) * 8 + 7, x1);
+      const int vy0 = max((__ffs(my) - 1) * 8, y0), vy1 = min((31 - __clz(my)) * 8 + 7, y1);
+      emit(s, (int)s.tri, vx0, vy0, vx1, vy1);
+    }
+    if (tid == 0) s_nq[par] = 0;
+    __syncthreads();   // the queue and its counter are free again
   }
   __syncthreads();
   if (tid == 0) {
@@ -605,8 +641,8 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     if (n > 0) {
       a.bbox[4 * f + 0] = s_bb[0]; a.bbox[4 * f + 1] = s_bb[1];
       a.bbox[4 * f + 2] = s_bb[2]; a.bbox[4 * f + 3] = s_bb[3];
-      a.worklist[atomicAdd(a.work_n, 1)] = f;
     }
+    if (n > 0 || a.list_all) a.worklist[atomicAdd(a.work_n, 1)] = f;
   }
 }
 
@@ -634,6 +670,7 @@ struct ContactArgs {
   int sensors_per_env;
   int kmax;
   int budget;                // region pixel budget (<= the compiled one)
+  FillArgs fill;             // fill.parts != 0: this kernel writes those parts of every listed frame first
 };
 #ifndef CT_BLOCK_N
 #define CT_BLOCK_N 512
@@ -745,7 +782,8 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   __shared__ int s_wsum[CT_BLOCK / 32];
   __shared__ float sM[12];
   __shared__ int s_hits, s_frame;
-  __shared__ int s_hb[4];  // bounds of the pixels that changed (hits dilated by the blur radius)
+  __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows)
+  __shared__ int s_sb[4];  // bounds of the hit pixels of the current sub-window's region
   __shared__ unsigned short s_q[CT_BLOCK / 32][64];  // per-warp queue of hit pixels waiting to be shaded
   __shared__ double s_rb[511];            // remove_bg: d / 255.0 + 0.5 for d = -255..255 (f64 divide once)
   __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
@@ -765,8 +803,13 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     const int f = s_frame;
     CT_T(0);
     if (f < 0) return;
-    if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const int K = a.counts[f];
+    // Fused fill: the frame's no-contact result (the parts tac_geom left to this kernel) streams out while
+    // the raster / shading work of the frame runs; the barriers below order these stores before the
+    // rewrite of the changed box.
+    if (a.fill.parts) fill_frame(a.fill, f, tid, CT_BLOCK);
+    if (K <= 0) continue;   // listed only to be filled
+    if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const Setup* list = a.setups + (size_t)f * a.kmax;
     // window that can change: union of the triangle boxes, dilated by the blur radius
     const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
@@ -813,7 +856,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
           }
         }
-        if (tid == 0) s_hits = 0;
+        if (tid == 0) { s_hits = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
         CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
@@ -1005,24 +1048,35 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             hx0 = __reduce_min_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1);
             hy0 = __reduce_min_sync(0xffffffffu, hy0); hy1 = __reduce_max_sync(0xffffffffu, hy1);
             if (lane == 0) {
-              atomicMin(&s_hb[0], hx0); atomicMax(&s_hb[2], hx1);
-              atomicMin(&s_hb[1], hy0); atomicMax(&s_hb[3], hy1);
+              atomicMin(&s_sb[0], hx0); atomicMax(&s_sb[2], hx1);
+              atomicMin(&s_sb[1], hy0); atomicMax(&s_sb[3], hy1);
             }
           }
         }
         __syncthreads();
         CT_T(4);
-        // --- 7-tap horizontal pass over the interior columns (BORDER_REFLECT_101 at the image edge).
-        // A thread produces 4 neighbouring outputs from one 10-value window.
-        const int iw = ix1 - tx + 1, ih = iy1 - ty + 1;
+        // Only pixels within the blur radius of a hit can differ from what tac_fill wrote (the difference
+        // image is 0 elsewhere): the changed box = hit box dilated by HALO, inside the interior.
+        const int bx0 = max(s_sb[0] - HALO, tx), bx1 = min(s_sb[2] + HALO, ix1);
+        const int by0 = max(s_sb[1] - HALO, ty), by1 = min(s_sb[3] + HALO, iy1);
+        if (tid == 0) {
+          s_hb[0] = min(s_hb[0], s_sb[0]); s_hb[1] = min(s_hb[1], s_sb[1]);
+          s_hb[2] = max(s_hb[2], s_sb[2]); s_hb[3] = max(s_hb[3], s_sb[3]);
+        }
+        if (bx0 > bx1 || by0 > by1) continue;   // hits only in this region's halo: they belong to a neighbour
+        // --- 7-tap horizontal pass over the changed columns (BORDER_REFLECT_101 at the image edge), for the
+        // rows the vertical pass will read.  A thread produces 4 neighbouring outputs from one 10-value window.
+        const int iw = bx1 - bx0 + 1, ih = by1 - by0 + 1;
         {
           const int nqx = (iw + 3) >> 2;
           const uint32_t inv_q = 0xffffffffu / (uint32_t)nqx + 1u;   // wraps to 0 for nqx == 1
-          for (int it = tid; it < RH * nqx; it += CT_BLOCK) {
-            const int ry = nqx == 1 ? it : (int)__umulhi((uint32_t)it, inv_q), qx = it - ry * nqx;
+          const int hr0 = by0 - HALO - ry0, nhr = ih + 2 * HALO;     // region rows [hr0, hr0 + nhr)
+          for (int it = tid; it < nhr * nqx; it += CT_BLOCK) {
+            const int rq = nqx == 1 ? it : (int)__umulhi((uint32_t)it, inv_q), qx = it - rq * nqx;
+            const int ry = hr0 + rq;
             const int py = ry0 + ry;
             if (py < 0 || py >= TH) continue;
-            const int px0 = tx + 4 * qx;
+            const int px0 = bx0 + 4 * qx;
             float win[10][NCH];
             const bool inner = px0 >= HALO && px0 + 3 + HALO < TW;
 #pragma unroll
@@ -1034,7 +1088,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              if (px0 + o > ix1) break;
+              if (px0 + o > bx1) break;
               float acc[NCH];
 #pragma unroll
               for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
@@ -1059,7 +1113,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
           const uint32_t inv_w = 0xffffffffu / (uint32_t)iw + 1u;    // wraps to 0 for iw == 1
           for (int it = tid; it < nqy * iw; it += CT_BLOCK) {
             const int qy = iw == 1 ? it : (int)__umulhi((uint32_t)it, inv_w), lx = it - qy * iw;
-            const int px = tx + lx, py0 = ty + 4 * qy;
+            const int px = bx0 + lx, py0 = by0 + 4 * qy;
             float win[10][NCH];
             const bool inner = py0 >= HALO && py0 + 3 + HALO < TH;
 #pragma unroll
@@ -1072,7 +1126,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               const int py = py0 + o;
-              if (py > iy1) break;
+              if (py > by1) break;
               float acc[NCH];
 #pragma unroll
               for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
@@ -1108,6 +1162,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
       const int oy0 = max((2 * fy_lo) / 7 - 1, 0), oy1 = min((2 * fy_hi) / 7 + 1, OBS_H - 1);
       const int ox0 = max((2 * hx0) / 7 - 1, 0), ox1 = min((2 * hx1) / 7 + 1, OBS_W - 1);
       const int nw = ox1 - ox0 + 1, nh = oy1 - oy0 + 1;
+      if (tid == 0) { CT_COUNT(15, 1); CT_COUNT(23, (hx1 - hx0 + 1) * (hy1 - hy0 + 1)); CT_COUNT(24, ww * wh); }
       float* ob = a.obs + (size_t)(f / a.sensors_per_env) * a.obs_env_stride +
                   (size_t)(f % a.sensors_per_env) * a.obs_sensor_stride;
       // One region held the whole window: every changed pixel's (colour - bg_real) sits in shared
@@ -1115,6 +1170,8 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
       const bool from_smem = NCH == 1 && nsx == 1 && nsy == 1;
       const uint32_t* s_delta = reinterpret_cast<const uint32_t*>(s_z);
       const int rx0 = wx0 - HALO, ry0 = wy0 - HALO;
+      // changed box of the (single) region: the vertical pass left colour - bg_real there, it is 0 elsewhere
+      const int cbx0 = max(hx0, wx0), cbx1 = min(hx1, wx1), cby0 = max(hy0, wy0), cby1 = min(hy1, wy1);
       for (int i = tid; i < nw * nh; i += CT_BLOCK) {
         const int oy = oy0 + i / nw, ox = ox0 + i % nw;
         // cv2 INTER_AREA, scale 3.5: taps for even/odd destination index
@@ -1133,7 +1190,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             int dl[3];
             if (from_smem) {
               uint32_t pk = (256u << 20) | (256u << 10) | 256u;
-              if (px >= wx0 && px <= wx1 && py >= wy0 && py <= wy1) pk = s_delta[2 * ((py - ry0) * RW + (px - rx0))];
+              if (px >= cbx0 && px <= cbx1 && py >= cby0 && py <= cby1) pk = s_delta[2 * ((py - ry0) * RW + (px - rx0))];
 #pragma unroll
               for (int c = 0; c < 3; ++c) dl[c] = (int)((pk >> (10 * c)) & 1023u) - 256;
             } else {
@@ -1199,6 +1256,16 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
 // =============================================================================================
 static int g_gray = 0;  // mirrors kc.gray of the last igi_tactile_set_sensor (one device per process)
 static int g_region_budget = 0;  // 0 = compiled budget
+#ifndef FILL_GEOM_PARTS
+#define FILL_GEOM_PARTS 7
+#endif
+static int g_fill_geom_parts = FILL_GEOM_PARTS;  // fill parts (1 colour, 2 gel_depth, 4 obs) written by tac_geom; the rest by tac_contact
+
+extern "C" int igi_tactile_set_fill_split(int geom_parts) {
+  IGI_REQUIRE(geom_parts >= 0 && geom_parts <= 7, "igi_tactile_set_fill_split: parts mask must be 0..7");
+  g_fill_geom_parts = geom_parts;
+  return IGI_OK;
+}
 
 extern "C" int igi_tactile_set_region_budget(int pixels) {
   IGI_REQUIRE(pixels == 0 || pixels >= (2 * HALO + 1) * (2 * HALO + 1), "igi_tactile_set_region_budget: need 0 or >= 49 pixels");
@@ -1310,6 +1377,10 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   const int stages = fr->stage_mask ? fr->stage_mask : (8 | 4);
   IGI_REQUIRE((stages & ~15) == 0 && !((stages & 8) && (stages & 3)),
               "igi_tactile_render: stage_mask 8 (fused geometry+fill) excludes bits 1 and 2");
+  // In the fused modes (no bit 1 / 2) the fill is split between the two kernels: tac_geom writes
+  // g_fill_geom_parts, tac_contact the rest (it then visits every live frame, not only those with candidates).
+  const bool fused = (stages & 3) == 0;
+  const int parts_geom = fused ? g_fill_geom_parts : 0, parts_contact = fused ? (7 & ~g_fill_geom_parts) : 0;
   // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
   if (stages & 9) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
   else IGI_CUDA(cudaMemsetAsync(sc->counters + 1, 0, sizeof(int32_t), s));
@@ -1319,6 +1390,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   fa.obs_env_stride = out->obs_env_stride; fa.obs_sensor_stride = out->obs_sensor_stride;
   fa.sensors_per_env = fr->sensors_per_env;
   fa.n_frames = F;
+  fa.parts = 7;
   GeomArgs g{};
   g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
@@ -1327,8 +1399,10 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
-  g.fused_fill = (stages & 8) ? 1 : 0;
+  g.fused_fill = (stages & 8) && parts_geom ? 1 : 0;
+  g.list_all = parts_contact ? 1 : 0;
   g.fill = fa;
+  g.fill.parts = parts_geom;
   if (stages & 9) {
     tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
     IGI_CHECK_LAUNCH("tac_geom");
@@ -1346,6 +1420,8 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   ca.obs_env_stride = out->obs_env_stride; ca.obs_sensor_stride = out->obs_sensor_stride;
   ca.sensors_per_env = fr->sensors_per_env;
   ca.kmax = sc->kmax;
+  ca.fill = fa;
+  ca.fill.parts = parts_contact;
   {
     const int compiled = g_gray ? CT_BUD_GRAY : CT_BUD_RGB;
     ca.budget = g_region_budget > 0 && g_region_budget < compiled ? g_region_budget : compiled;

@@ -27,6 +27,7 @@ c = list(out)
 nf = int((task.tactile_engine.contact_counts() > 0).sum().item())
 print(f"frames {nf}: per frame rows {c[9]/nf:.0f}, span pixels {c[10]/nf:.0f}, shaded px {c[11]/nf:.0f}, "
       f"regions x chunks {c[12]/nf:.2f}, region px {c[13]/nf:.0f}, tris {c[14]/nf:.0f}")
+print(f"frames with hits {c[15]} of {nf}; per hit frame: changed box {c[23]/max(c[15],1):.0f} px, dirty window {c[24]/max(c[15],1):.0f} px")
 F = 3 * E
 print(f"geom per frame (all {F}): clusters kept {c[16]/F:.1f} of {c[17]/F:.1f}, faces in {c[18]/F:.0f}, front-facing {c[19]/F:.0f}, "
       f"near gel {c[20]/F:.0f}, on screen {c[21]/F:.0f}, pass hi-z {c[22]/F:.0f} (incl. warp-queue recomputation), emitted {float(task.tactile_engine.contact_counts().clamp(min=0).float().mean()):.0f}")

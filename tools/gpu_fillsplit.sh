@@ -1,0 +1,12 @@
+# bench kernel table for each fill split (parts written by tac_geom; rest by tac_contact)
+for v in 7 0 5 2 4; do
+  echo "=== geom parts $v"
+  IGI_NVCC_EXTRA="-DFILL_GEOM_PARTS=$v" python -m isaacgyminsertion_b200.build --force > /dev/null 2>&1 || { echo build failed; continue; }
+  python -m pytest tests/test_tactile_gpu.py -m gpu -x -q 2>&1 | tail -1
+  python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/v_bench.json 2> gpurun_out/v_bench.err; tail -3 gpurun_out/v_bench.err
+  python - <<'PY'
+import json
+d=json.load(open('gpurun_out/v_bench.json'))
+print("ms/step",round(d["ms_per_step"],3), {k:round(v["ms"],3) for k,v in d["kernels"].items() if k.startswith("tac")})
+PY
+done
