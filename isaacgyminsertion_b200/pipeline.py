@@ -81,13 +81,10 @@ class HostObsPipeline:
         task.plug_pos, task.plug_quat = d["ppos"], d["pquat"]
         task.cam_renders, task.seg_renders = d["depth"], d["seg"]
         up = self._ones if update is None else update
-        if task.tactile:
-            task.update_tactile(up, up)
-        if task.pcl_cam:
-            if self.socket_every_step:
-                task._socket_pending = True
-                task.got_socket.zero_()
-            task.update_external_cam(up, up, up, self._zeros, self._zeros)
+        if task.pcl_cam and self.socket_every_step:
+            task._socket_pending = True
+            task.got_socket.zero_()
+        task.compute_observations(up, up, up, up, up, self._zeros, self._zeros)
         self.d_out[slot].copy_(task.obs_packed)
         self.ev_done[slot].record(cur)
         # download

@@ -84,6 +84,7 @@ class SyntheticGym:
         origins_all = env_origins(total)
         sl = slice(global_env_offset, global_env_offset + n_envs)
         self.n_envs = n_envs
+        self.global_env_offset = global_env_offset
         self.width, self.height = width, height
         self.hfov = hfov_all[sl].astype(np.float64)
         self.origins = origins_all[sl]
@@ -151,8 +152,8 @@ def external_camera_frames(gym, plug_pos, plug_quat, socket_pos, seed=0, miss_fr
     plug_pos (N,3), plug_quat (N,4 xyzw), socket_pos (N,3) are env-local.
     Returns depth (N,H,W) f32 (negative metric z, -inf on miss) and seg (N,H,W) i32.
     """
-    rng = np.random.default_rng(seed + 7919)
     N, H, W = gym.n_envs, gym.height, gym.width
+    g0 = getattr(gym, "global_env_offset", 0)
     depth = np.empty((N, H, W), dtype=np.float32)
     seg = np.empty((N, H, W), dtype=np.int32)
     vv, uu = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
@@ -190,7 +191,8 @@ def external_camera_frames(gym, plug_pos, plug_quat, socket_pos, seed=0, miss_fr
         t_best = np.where(upd, t, t_best)
         s_best = np.where(upd, SEG_KUKA, s_best)
         # a few dropped returns (ray misses -> -inf), also on object pixels
-        drop = rng.random(H * W) < miss_fraction
+        # (drawn per GLOBAL env id, so an env's frame does not depend on how the envs are sharded)
+        drop = np.random.default_rng([seed + 7919, g0 + e]).random(H * W) < miss_fraction
         t_best = np.where(drop, np.inf, t_best)
         depth[e] = (-t_best).astype(np.float32).reshape(H, W)
         seg[e] = s_best.reshape(H, W)

@@ -52,7 +52,7 @@ class PointCloudAugmentations:
 class FactoryTaskInsertionTactileObs:
     def __init__(self, num_envs, gym, mesh_ids, bg_ids=None, device="cuda", num_points=400, num_points_socket=400,
                  tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=2048,
-                 strict_rng=True, pcl_noise_enabled=False):
+                 strict_rng=True, pcl_noise_enabled=False, overlap_streams=True):
         self.device = torch.device(device)
         self.num_envs = num_envs
         self.fingertips = ["finger_1_3", "finger_2_3", "finger_3_3"]   # factory_env_insertion.py:748
@@ -61,6 +61,8 @@ class FactoryTaskInsertionTactileObs:
         self.sampler = sampler
         self.strict_rng = strict_rng
         self.pcl_noise_enabled = pcl_noise_enabled   # RNG-defined augmentation
+        self.overlap_streams = overlap_streams       # compute_observations: pcl path on a side stream
+        self._side = None
         dev = self.device
         N = num_envs
         # packed observation rows: [tactile (3*2048) | pcl (2400)]
@@ -171,7 +173,7 @@ class FactoryTaskInsertionTactileObs:
             if self.pcl_noise_enabled:
                 self.socket_pcl.copy_(torch.where(noisy[:, None, None], self.pcl_process.augment(
                     self.socket_pcl, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), self.socket_pcl))
-            self.got_socket[restarted] = 1
+            self.got_socket.masked_fill_(restarted[:, None], 1)      # no boolean-index host sync
             update = update | restarted
             self._socket_pending = False
         if plug_pts is self._plug_pts and self._both_pts is not None:
@@ -181,6 +183,35 @@ class FactoryTaskInsertionTactileObs:
         self.pcl.copy_(torch.where(update[:, None], merged, self.pcl))
         self.pcl_queue[:, 1:] = self.pcl_queue[:, :-1].clone().detach()                              # :1046-1048
         self.pcl_queue[:, 0, ...] = self.pcl
+
+    # ------------------------------------------------------------------ both parts of one env step
+    @torch.no_grad()
+    def compute_observations(self, tactile_update_freq, tactile_update_delay, img_update_freq, img_update,
+                             seg_update, seg_add_noise, pcl_add_noise):
+        """Observation part of `compute_observations` (factory_task_insertion.py:862-887): `update_tactile`
+        then `update_external_cam` with the masks the reference draws there.  The two parts share no
+        data, so the point-cloud kernels (a latency chain of dependent FPS picks that leaves most issue
+        slots idle) are enqueued on a high-priority side stream and run underneath the tactile kernels;
+        the current stream waits for them before returning, so callers see the reference's ordering."""
+        both = self.tactile and self.pcl_cam and self.overlap_streams
+        if not both:
+            if self.tactile:
+                self.update_tactile(tactile_update_freq, tactile_update_delay)
+            if self.pcl_cam:
+                self.update_external_cam(img_update_freq, img_update, seg_update, seg_add_noise, pcl_add_noise)
+            return self.obs_packed
+        cur = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record(cur)
+        self._side.wait_event(self._ev_fork)
+        with torch.cuda.stream(self._side):
+            self.update_external_cam(img_update_freq, img_update, seg_update, seg_add_noise, pcl_add_noise)
+            self._ev_join.record(self._side)
+        self.update_tactile(tactile_update_freq, tactile_update_delay)
+        cur.wait_event(self._ev_join)
+        return self.obs_packed
 
     def _sample(self, pts, cnt, any_, cls, m, out):
         eng = self.pcl_generator.engine
