@@ -224,6 +224,65 @@ int igi_tactile_set_fill_split(int geom_parts);
 int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,
                     int64_t obs_stride, void* stream);
 
+/* --------------------------------------------------------------------------
+ * (S) stages next to the hot path: image observations of the external camera,
+ * RNG-defined noise, history queues, and the student's first preprocessing step.
+ * Random numbers are Philox4x32-10 keyed by `seed`, counter = (global element index, step,
+ * stream id): results depend on the GLOBAL env id (env0 + local env), not on how envs are
+ * sharded over GPUs.  The reference draws from torch's global generators over compacted rows
+ * (distribution-level parity only); oracle/student.py restates the same Philox so
+ * kernel == oracle bit for bit on the integer parts.
+ * -------------------------------------------------------------------------- */
+
+/* S1  depth / segmentation image observations.
+ * Replaces: update_external_cam depth_cam + seg_cam branches  factory_task_insertion.py:925-943
+ *           DepthImageProcessor.process_depth_image / normalize_depth_image / add_seg_noise
+ *                                                         tasks/factory_tactile/factory_utils.py:23-37,55-72
+ *   image_buf[e] = ((-clip(depth[e] + dis_noise*2*(U-0.5), -far, -near)) - near) / (far - near)  where update[e]
+ *   seg_buf[e]   = seg[e]                                                               where update_seg[e]
+ *   seg_buf[e][(seg > 0) & (U' < flip_prob)] = 0                       where seg_noise[e] & update_seg[e]
+ *   depth (n_envs,npix) f32, seg (n_envs,npix) i32; update / update_seg / seg_noise (n_envs) u8 or NULL
+ *   (NULL update* = every row, NULL seg_noise = none); image_buf / seg_buf may be NULL (stage off).
+ *   npix % 4 == 0, rows 16-byte aligned. */
+int igi_cam_image_obs(const float* depth, const int32_t* seg, const uint8_t* update, const uint8_t* update_seg,
+                      const uint8_t* seg_noise, int n_envs, int npix, long long env0, double dis_noise,
+                      double far_clip, double near_clip, float flip_prob, uint64_t seed, uint32_t step,
+                      float* image_buf, int32_t* seg_buf, void* stream);
+
+/* S2  PointCloudAugmentations.random_noise, in place, under a per-env mask.
+ * Replaces: factory_utils.py:93-100 as called at factory_task_insertion.py:966-969,979-982
+ *   p += clamp(N(0,1)*sigma, +-clip) * (U < noise_prob);  p += clamp(pcl_noise[e]*const_noise, +-clip)
+ *   pts: env e's (n_pts,3) f32 at pts + e*env_stride floats; mask (n_envs) u8 or NULL (all);
+ *   pcl_noise (n_envs,3) f32 = the task's pcl_pos_noise. */
+int igi_pcl_noise(float* pts, int64_t env_stride, int n_envs, int n_pts, const uint8_t* mask, const float* pcl_noise,
+                  long long env0, float sigma, float noise_clip, float const_noise, float noise_prob, uint64_t seed,
+                  uint32_t step, void* stream);
+
+/* S3  RunningMeanStd.forward on (rows, channels) f32, per_channel=False.
+ * Replaces: algo/models/running_mean_std.py:60-93 as called by ExtrinsicAdapt.process_obs
+ *           (algo/ext_adapt/ext_adapt.py:405: pcl.reshape(-1, 3); :421: student_obs)
+ *   training != 0: running_mean/var/count (f64, device) are first updated with this batch's mean and
+ *   unbiased variance (parallel-variance update :47-57), then used.
+ *   mode 0: clamp((x - mean.float()) / sqrt(var.float() + eps), -5, 5);  1 (norm_only): x / sqrt(...);
+ *   2 (unnorm=True): sqrt(...) * clamp(x, -5, 5) + mean.  y may alias x.
+ *   scratch: igi_rms_scratch_bytes(channels) bytes, zeroed once by the caller, needed when training. */
+long long igi_rms_scratch_bytes(int channels);
+int igi_rms_forward(const float* x, long long rows, int channels, double* running_mean, double* running_var,
+                    double* count, float epsilon, int training, int mode, float* y, void* scratch, void* stream);
+
+/* S4  seg / depth-image masking of the student's inputs.
+ * Replaces: ExtrinsicAdapt.process_obs  algo/ext_adapt/ext_adapt.py:391-396
+ *   valid = (seg == obj_id) | (seg == socket_id);  seg_out = distinct ? seg*valid : valid;  img_out = img*valid
+ *   n elements (multiple of 4), f32; img / img_out may be NULL; outputs may alias inputs. */
+int igi_seg_valid_mask(const float* seg, const float* img, long long n, float obj_id, float socket_id, int distinct,
+                       float* seg_out, float* img_out, void* stream);
+
+/* S5  history queue push: queue[:, 1:] = queue[:, :-1]; queue[:, 0] = x (converted to f32).
+ * Replaces: factory_task_insertion.py:512-513 (tactile_queue), :1046-1056 (pcl / img / seg queues)
+ *   queue (n_envs, hist_len, row_len) f32; x row e at x + e*x_stride elements, f32 or (x_is_int32) i32. */
+int igi_queue_push(float* queue, const void* x, int x_is_int32, int64_t x_stride, int n_envs, int hist_len,
+                   long long row_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ def load():
     lib.igi_last_error.restype = _c.c_char_p
     for name in declared_symbols():
         fn = getattr(lib, name)  # raises AttributeError if a declared symbol is not exported
-        if name == "igi_launch_count":
+        if name in ("igi_launch_count", "igi_rms_scratch_bytes"):
             fn.restype = _c.c_longlong
         elif name not in ("igi_last_error",):
             fn.restype = _c.c_int

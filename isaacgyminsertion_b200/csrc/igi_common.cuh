@@ -82,6 +82,10 @@ __device__ __forceinline__ void igi_bulk_s2g(void* gdst, const void* smem_src, u
 __device__ __forceinline__ void igi_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // waits until the bulk groups of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void igi_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// waits until the bulk groups of this thread have COMPLETED (their global writes are performed)
+__device__ __forceinline__ void igi_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// ... until at most the most recent bulk group of this thread is still pending
+__device__ __forceinline__ void igi_bulk_wait1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void igi_fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

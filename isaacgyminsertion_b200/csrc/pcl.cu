@@ -31,21 +31,63 @@ struct CompactParams {
 // for 54x96) are staged into shared memory with two 1-D bulk async copies (TMA
 // engine) that complete on an mbarrier; every class (plug, socket) is then
 // produced from the staged tile, so HBM sees each input byte once.
-// Compaction keeps row-major pixel order (pcl_utils.py:71-72 boolean indexing):
-// each thread owns a contiguous pixel chunk, a block-wide exclusive scan of the
-// per-thread keep counts gives the output slot.
+// Compaction keeps row-major pixel order (pcl_utils.py:71-72 boolean indexing).  A lane owns 4
+// consecutive pixels (one 128-bit shared load of depth, one of seg), a warp 128:
+//   phase A  lanes unproject / transform / box-test only their pixels of a wanted class (most of the
+//            image is background: two compares per pixel) and leave a 4-bit keep mask per class
+//   scan     block-wide exclusive scan of the per-lane keep counts, one class after the other
+//   phase B  lanes with kept pixels recompute the points (same instruction sequence, same bits) and
+//            store them at their offsets
+struct CompactEval {
+  const float* A;   // ext, row-vector: w = [px,py,pz,1] @ A
+  const float* B;   // inverse(env_to_global): o = w @ B^T
+  const float* uvx;
+  const float* uvy;
+  float uvz, depth_max;
+  int W, has_box;
+  uint32_t inv_w;   // floor(i / W) = umulhi(i, inv_w) for i < 2^16
+  float box[6];
+  // point of pixel i with (masked) depth d; false when dropped by `d > -depth_max` or the box
+  __device__ __forceinline__ bool operator()(int i, float d, float* o) const {
+    if (!(depth_max < 0.0f) && !(d > -depth_max)) return false;
+    const int v = (int)__umulhi((uint32_t)i, inv_w), u = i - v * W;
+    const float px = __fmul_rn(uvx[u], d);
+    const float py = __fmul_rn(uvy[v], d);
+    const float pz = __fmul_rn(uvz, d);
+    // w = [px py pz 1] @ ext   (pcl_utils.py:77-83)
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = fmaf(pz, A[8 + j], fmaf(py, A[4 + j], fmaf(px, A[j], A[12 + j])));
+    // o = w @ inverse(env_to_global)^T   (pcl_utils.py:84-85)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o[j] = fmaf(w[3], B[4 * j + 3], fmaf(w[2], B[4 * j + 2], fmaf(w[1], B[4 * j + 1], w[0] * B[4 * j])));
+    if (has_box)
+      return (o[0] >= box[0]) && (o[0] <= box[1]) && (o[1] >= box[2]) && (o[1] <= box[3]) && (o[2] >= box[4]) &&
+             (o[2] <= box[5]);
+    return true;
+  }
+};
+
 __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NW = kCompactBlock / 32;
   const int npix = p.H * p.W;
+  const int nq = (npix + 3) >> 2;                       // 4-pixel entries
+  const int seg_off = (npix * 4 + 15) & ~15;
   float* s_depth = reinterpret_cast<float*>(smem_raw);
-  int32_t* s_seg = reinterpret_cast<int32_t*>(smem_raw + (size_t)npix * 4);
+  int32_t* s_seg = reinterpret_cast<int32_t*>(smem_raw + seg_off);
+  // per entry: keep masks (4 bits per class), then per class its exclusive output offset
+  uint16_t* s_keep = reinterpret_cast<uint16_t*>(smem_raw + 2 * (size_t)seg_off);
   __shared__ uint64_t s_bar;
-  __shared__ int s_warp_tot[kCompactBlock / 32];
-  __shared__ int s_warp_any[kCompactBlock / 32];
+  __shared__ int s_wsum[NW];
+  __shared__ int s_warp_any[NW];
+  __shared__ int s_carry;
   __shared__ float s_m[32];  // ext (16) + e2g_inv (16)
 
   const int env = blockIdx.x;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const float* g_depth = p.depth + (size_t)env * npix;
   const int32_t* g_seg = p.seg ? p.seg + (size_t)env * npix : nullptr;
 
@@ -72,16 +114,20 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   if (p.use_bulk) igi_mbar_wait(&s_bar, 0);
   __syncthreads();
 
-  const float* uvx = p.uvx + (size_t)env * p.W;
-  const float* uvy = p.uvy + (size_t)env * p.H;
-  const float uvz = p.uvz[env];
-  const float* A = s_m;       // row-vector: w = [px,py,pz,1] @ A
-  const float* B = s_m + 16;  // o = w @ B^T
-
-  const int chunk = (npix + kCompactBlock - 1) / kCompactBlock;
-  const int lo = min(tid * chunk, npix);
-  const int hi = min(lo + chunk, npix);
-  const int lane = tid & 31, warp = tid >> 5;
+  CompactEval ev;
+  ev.A = s_m; ev.B = s_m + 16;
+  ev.uvx = p.uvx + (size_t)env * p.W;
+  ev.uvy = p.uvy + (size_t)env * p.H;
+  ev.uvz = p.uvz[env];
+  ev.depth_max = p.depth_max;
+  ev.W = p.W; ev.has_box = p.has_box;
+  ev.inv_w = 0xffffffffu / (uint32_t)p.W + 1u;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ev.box[k] = p.box[k];
+  int sid[kMaxClasses];
+#pragma unroll
+  for (int c = 0; c < kMaxClasses; ++c) sid[c] = p.seg_ids[c];
+  const int NC = p.n_classes;
 
   // A masked-out pixel with finite depth becomes d = +-0 (pcl_utils.py / task :956-959) and maps to the
   // camera centre whatever its (u, v): w = ext[3,:], o = w @ e2g_inv^T.  Signs of zero do not change
@@ -90,6 +136,8 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   // masked-out miss (-inf * 0 = NaN) is dropped by `d > -depth_max` either way.
   bool zero_kept = true;
   if (g_seg && p.has_box) {
+    const float* A = ev.A;
+    const float* B = ev.B;
     float o[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
@@ -98,81 +146,97 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
                 (o[2] >= p.box[4]) && (o[2] <= p.box[5]);
   }
 
-  for (int c = 0; c < p.n_classes; ++c) {
-    const int sid = p.seg_ids[c];
-    // pass 1: count kept pixels of this thread's chunk; pass 2: write them.
-    int kept = 0;
-    int any = 0;
-    float* out = p.out_pts + ((size_t)env * p.n_classes + c) * (size_t)npix * 3;
-    int base = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      int slot = base;
-      for (int i = lo; i < hi; ++i) {
-        float d = s_depth[i];
-        if (g_seg) {
-          const bool mine = s_seg[i] == sid;
-          if (!mine && !zero_kept) continue;
-          d = __fmul_rn(d, mine ? 1.0f : 0.0f);  // -inf*0 = NaN, finite*0 = -0
-        }
-        bool ok = (p.depth_max < 0.0f) ? true : (d > -p.depth_max);
-        if (!ok) continue;
-        const int v = i / p.W, u = i - v * p.W;
-        const float px = __fmul_rn(uvx[u], d);
-        const float py = __fmul_rn(uvy[v], d);
-        const float pz = __fmul_rn(uvz, d);
-        // w = [px py pz 1] @ ext   (pcl_utils.py:77-83)
-        float w[4];
+  // ---- phase A: keep masks.  Entry q = pixels 4q .. 4q+3; thread tid owns entries tid, tid + 256, ...
+  uint32_t anybits = 0;  // bit c: this thread kept a point of class c with a non-zero coordinate
+  for (int q = tid; q < nq; q += kCompactBlock) {
+    const float4 d4 = reinterpret_cast<const float4*>(s_depth)[q];
+    int4 s4 = make_int4(0, 0, 0, 0);
+    if (g_seg) s4 = reinterpret_cast<const int4*>(s_seg)[q];
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    const int sg[4] = {s4.x, s4.y, s4.z, s4.w};
+    uint32_t keep = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          w[j] = fmaf(pz, A[8 + j], fmaf(py, A[4 + j], fmaf(px, A[j], A[12 + j])));
-        // o = w @ inverse(env_to_global)^T   (pcl_utils.py:84-85)
-        float o[3];
+    for (int c = 0; c < kMaxClasses; ++c) {
+      if (c >= NC) break;
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-          o[j] = fmaf(w[3], B[4 * j + 3], fmaf(w[2], B[4 * j + 2], fmaf(w[1], B[4 * j + 1], w[0] * B[4 * j])));
-        if (p.has_box) {
-          ok = (o[0] >= p.box[0]) && (o[0] <= p.box[1]) && (o[1] >= p.box[2]) && (o[1] <= p.box[3]) &&
-               (o[2] >= p.box[4]) && (o[2] <= p.box[5]);
-          if (!ok) continue;
+      for (int k = 0; k < 4; ++k) {
+        const int i = 4 * q + k;
+        const bool mine = g_seg ? sg[k] == sid[c] : true;
+        if (i < npix && (mine || zero_kept)) {
+          const float dd = g_seg ? __fmul_rn(d[k], mine ? 1.0f : 0.0f) : d[k];  // -inf*0 = NaN, finite*0 = -0
+          float o[3];
+          if (ev(i, dd, o)) {
+            keep |= 1u << (4 * c + k);
+            if ((o[0] != 0.0f) | (o[1] != 0.0f) | (o[2] != 0.0f)) anybits |= 1u << c;
+          }
         }
-        if (pass == 0) {
-          ++kept;
-          any |= (o[0] != 0.0f) | (o[1] != 0.0f) | (o[2] != 0.0f);
-        } else {
-          out[(size_t)slot * 3 + 0] = o[0];
-          out[(size_t)slot * 3 + 1] = o[1];
-          out[(size_t)slot * 3 + 2] = o[2];
+      }
+    }
+    s_keep[q] = (uint16_t)keep;
+  }
+  {
+    uint32_t wany = 0;
+    for (int c = 0; c < NC; ++c)
+      if (__any_sync(0xffffffffu, (anybits >> c) & 1u)) wany |= 1u << c;
+    if (lane == 0) s_warp_any[warp] = (int)wany;
+  }
+  __syncthreads();
+
+  // ---- per class: block scan over the entries in pixel order (256 consecutive entries per round, so
+  // the scan order is the pixel order), then phase B for that class
+  for (int c = 0; c < NC; ++c) {
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    float* out = p.out_pts + ((size_t)env * NC + c) * (size_t)npix * 3;
+    const int sid_c = p.seg_ids[c];
+    for (int q0 = 0; q0 < nq; q0 += kCompactBlock) {
+      const int q = q0 + tid;
+      const uint32_t m = q < nq ? (s_keep[q] >> (4 * c)) & 15u : 0u;
+      const int cnt = __popc(m);
+      int incl = cnt;
+#pragma unroll
+      for (int sft = 1; sft < 32; sft <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, sft);
+        if (lane >= sft) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int t = s_wsum[w];
+        if (w < warp) woff += t;
+        total += t;
+      }
+      int slot = s_carry + woff + incl - cnt;
+      if (m) {
+        const float4 d4 = reinterpret_cast<const float4*>(s_depth)[q];
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!((m >> k) & 1u)) continue;
+          const int i = 4 * q + k;
+          float dd = d[k];
+          if (g_seg) dd = __fmul_rn(dd, s_seg[i] == sid_c ? 1.0f : 0.0f);
+          float o[3];
+          ev(i, dd, o);
+          float* dst = out + (size_t)slot * 3;
+          dst[0] = o[0];
+          dst[1] = o[1];
+          dst[2] = o[2];
           ++slot;
         }
       }
-      if (pass == 0) {
-        // block-wide exclusive scan of `kept`
-        int incl = kept;
+      __syncthreads();   // everyone has read s_carry / s_wsum
+      if (tid == 0) s_carry += total;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int bany = 0;
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-          int t = __shfl_up_sync(0xffffffffu, incl, s);
-          if (lane >= s) incl += t;
-        }
-        const int wany = __any_sync(0xffffffffu, any);
-        __syncthreads();  // previous class finished reading s_warp_tot
-        if (lane == 31) s_warp_tot[warp] = incl;
-        if (lane == 0) s_warp_any[warp] = wany;
-        __syncthreads();
-        int woff = 0, total = 0, bany = 0;
-#pragma unroll
-        for (int wi = 0; wi < kCompactBlock / 32; ++wi) {
-          const int t = s_warp_tot[wi];
-          if (wi < warp) woff += t;
-          total += t;
-          bany |= s_warp_any[wi];
-        }
-        base = woff + incl - kept;
-        if (tid == 0) {
-          p.out_count[(size_t)env * p.n_classes + c] = total;
-          p.out_any[(size_t)env * p.n_classes + c] = bany;
-        }
-      }
+      for (int w = 0; w < NW; ++w) bany |= (s_warp_any[w] >> c) & 1;
+      p.out_count[(size_t)env * NC + c] = s_carry;
+      p.out_any[(size_t)env * NC + c] = bany;
     }
   }
 }
@@ -667,8 +731,8 @@ extern "C" int igi_pcl_compact(const float* depth, const int32_t* seg, const int
   p.has_box = box != nullptr;
   if (box) for (int i = 0; i < 6; ++i) p.box[i] = box[i];
   const size_t npix = (size_t)H * W;
-  const size_t smem = npix * 8;
-  IGI_REQUIRE(smem <= 200 * 1024, "igi_pcl_compact: image too large for one CTA (%d x %d)", H, W);
+  const size_t smem = 2 * ((npix * 4 + 15) & ~(size_t)15) + ((npix + 3) / 4) * 2 + 16;
+  IGI_REQUIRE(smem <= 200 * 1024 && npix < 65536, "igi_pcl_compact: image too large for one CTA (%d x %d)", H, W);
   p.use_bulk = ((npix * 4) % 16 == 0) && ((uintptr_t)depth % 16 == 0) && (!seg || (uintptr_t)seg % 16 == 0);
   static bool attr_set = false;
   if (!attr_set) {

@@ -681,6 +681,9 @@ struct ContactArgs {
 #ifndef CT_BUD_N
 #define CT_BUD_N 12288
 #endif
+#ifndef CT_ZERO_BYTES
+#define CT_ZERO_BYTES 4096
+#endif
 constexpr int CT_BLOCK = CT_BLOCK_N;
 constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
 static_assert(CT_CHUNK % CT_BLOCK_N == 0, "CT_CHUNK must be a multiple of the block size");
@@ -781,33 +784,71 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   __shared__ int s_off[CT_CHUNK];
   __shared__ int s_wsum[CT_BLOCK / 32];
   __shared__ float sM[12];
-  __shared__ int s_hits, s_frame;
+  __shared__ int s_hits, s_frame, s_next;
   __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows)
   __shared__ int s_sb[4];  // bounds of the hit pixels of the current sub-window's region
   __shared__ unsigned short s_q[CT_BLOCK / 32][64];  // per-warp queue of hit pixels waiting to be shaded
   __shared__ double s_rb[511];            // remove_bg: d / 255.0 + 0.5 for d = -255..255 (f64 divide once)
   __shared__ float s_dxp[TW], s_dyp[TH];  // ray-slope tables (per-lane indexing would serialise in the constant cache)
+  __shared__ __align__(16) float s_zero[CT_ZERO_BYTES / 4];  // source of the asynchronous gel_depth = 0 fill
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CT_BLOCK / 32;
   for (int i = tid; i < TW; i += CT_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
   for (int i = tid; i < 511; i += CT_BLOCK) s_rb[i] = (double)(i - 255) / 255.0 + 0.5;
+  for (int i = tid; i < CT_ZERO_BYTES / 4; i += CT_BLOCK) s_zero[i] = 0.0f;
+  igi_fence_proxy_async();   // the zeros must be visible to the bulk-copy (async) proxy
   const float span_x0 = k_dxp[0], span_kx = (float)(TW - 1) / (k_dxp[TW - 1] - k_dxp[0]);
+  // gel_depth = 0 of one frame (200 704 B of zeros): a few lanes of every warp hand 4 KB pieces of the zero
+  // buffer to the bulk-copy engine (shared -> global), which costs this issue-bound kernel no store
+  // instructions.  Every thread commits one (possibly empty) bulk group per call.
+  auto zero_fill_async = [&](int frame) {
+    if ((a.fill.parts & 2) && a.fill.gel_depth && frame >= 0) {
+      constexpr int NB = TW * TH * 4 / CT_ZERO_BYTES;
+      static_assert(NB * CT_ZERO_BYTES == TW * TH * 4, "zero buffer must divide the gel_depth frame");
+      constexpr int PER_WARP = (NB + NW - 1) / NW;
+      const int i = warp * PER_WARP + lane;
+      if (lane < PER_WARP && i < NB) {
+        char* dst = reinterpret_cast<char*>(a.fill.gel_depth + (size_t)frame * TW * TH);
+        igi_bulk_s2g(dst + (size_t)i * CT_ZERO_BYTES, s_zero, CT_ZERO_BYTES);
+      }
+    }
+    igi_bulk_commit();
+  };
+  // Work items are fetched ONE FRAME AHEAD: the zero fill of the next frame is issued when the current
+  // frame starts, so it has a whole frame time to land before that frame's first gel_depth write.
+  if (tid == 0) {
+    const int w = atomicAdd(a.cursor, 1);
+    s_next = (w < *a.work_n) ? a.worklist[w] : -1;
+  }
+  __syncthreads();
+  zero_fill_async(s_next);
   for (;;) {
     __syncthreads();
     if (tid == 0) {
-      const int w = atomicAdd(a.cursor, 1);
-      s_frame = (w < *a.work_n) ? a.worklist[w] : -1;
+      s_frame = s_next;
+      if (s_next >= 0) {
+        const int w = atomicAdd(a.cursor, 1);
+        s_next = (w < *a.work_n) ? a.worklist[w] : -1;
+      }
       s_hb[0] = TW; s_hb[1] = TH; s_hb[2] = -1; s_hb[3] = -1;
     }
     __syncthreads();
     const int f = s_frame;
     CT_T(0);
-    if (f < 0) return;
+    if (f < 0) {
+      igi_bulk_wait0();   // s_zero must outlive the copies that read it
+      return;
+    }
+    zero_fill_async(s_next);
     const int K = a.counts[f];
-    // Fused fill: the frame's no-contact result (the parts tac_geom left to this kernel) streams out while
-    // the raster / shading work of the frame runs; the barriers below order these stores before the
-    // rewrite of the changed box.
-    if (a.fill.parts) fill_frame(a.fill, f, tid, CT_BLOCK);
+    // Fused fill: the other parts of the frame's no-contact result that tac_geom left to this kernel go out
+    // with plain stores while the raster / shading work of the frame runs; the barriers below order them
+    // before the rewrite of the changed box.
+    if (a.fill.parts & ~2) {
+      FillArgs fa = a.fill;
+      fa.parts &= ~2;
+      fill_frame(fa, f, tid, CT_BLOCK);
+    }
     if (K <= 0) continue;   // listed only to be filled
     if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const Setup* list = a.setups + (size_t)f * a.kmax;
@@ -971,6 +1012,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
           }
         }
+        igi_bulk_wait1();   // this frame's zero fill has landed; only the next frame's group may still be in flight
         __syncthreads();
         CT_T(3);
         if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
@@ -1257,7 +1299,7 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
 static int g_gray = 0;  // mirrors kc.gray of the last igi_tactile_set_sensor (one device per process)
 static int g_region_budget = 0;  // 0 = compiled budget
 #ifndef FILL_GEOM_PARTS
-#define FILL_GEOM_PARTS 7
+#define FILL_GEOM_PARTS 5
 #endif
 static int g_fill_geom_parts = FILL_GEOM_PARTS;  // fill parts (1 colour, 2 gel_depth, 4 obs) written by tac_geom; the rest by tac_contact
 
