@@ -179,6 +179,8 @@ typedef struct IgiTactileFrames {
 typedef struct IgiTactileScratch {
   float* M;                     /* (F,12) object->camera matrices */
   void* setups;                 /* (F,kmax) 64-byte triangle setup records */
+  void* normals;                /* (F,kmax) 48-byte records: camera-frame vertex normals of the triangle in
+                                   the same slot of `setups` (interpolated per fragment when shading) */
   int32_t* counts;              /* (F) */
   int32_t* bbox;                /* (F,4) */
   int32_t* worklist;            /* (F) */

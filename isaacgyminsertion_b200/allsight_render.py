@@ -68,7 +68,7 @@ class IgiTactileFrames(_c.Structure):
 
 
 class IgiTactileScratch(_c.Structure):
-    _fields_ = [("M", _c.c_void_p), ("setups", _c.c_void_p), ("counts", _c.c_void_p), ("bbox", _c.c_void_p),
+    _fields_ = [("M", _c.c_void_p), ("setups", _c.c_void_p), ("normals", _c.c_void_p), ("counts", _c.c_void_p), ("bbox", _c.c_void_p),
                 ("worklist", _c.c_void_p), ("counters", _c.c_void_p), ("kmax", _c.c_int32)]
 
 
@@ -299,6 +299,7 @@ class BatchedAllSight:
         # scratch
         self._M = torch.empty((self.F, 12), dtype=torch.float32, device=dev)
         self._setups = torch.empty((self.F, self.kmax, 16), dtype=torch.int32, device=dev)
+        self._normals = torch.empty((self.F, self.kmax, 12), dtype=torch.float32, device=dev)
         self._counts = torch.zeros((self.F,), dtype=torch.int32, device=dev)
         self._bbox = torch.zeros((self.F, 4), dtype=torch.int32, device=dev)
         self._work = torch.zeros((self.F,), dtype=torch.int32, device=dev)
@@ -353,6 +354,7 @@ class BatchedAllSight:
         st.obs_empty, st.grid, st.hiz = self.obs_empty.data_ptr(), self._grid.data_ptr(), self._hiz.data_ptr()
         sc = IgiTactileScratch()
         sc.M, sc.setups, sc.counts = self._M.data_ptr(), self._setups.data_ptr(), self._counts.data_ptr()
+        sc.normals = self._normals.data_ptr()
         sc.bbox, sc.worklist, sc.counters, sc.kmax = (self._bbox.data_ptr(), self._work.data_ptr(),
                                                       self._counters.data_ptr(), self.kmax)
         self._m, self._st, self._sc = m, st, sc

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) pcl_noise_kernel(float* pts, int64_t env_
 }
 
 // ---- S3 ------------------------------------------------------------------------------------------
-constexpr int RMS_MAX_C = 16;
+constexpr int RMS_MAX_C = 256;   // <= RMS_BLOCK: one thread per channel folds the CTA partials
 constexpr int RMS_GRID = 592;   // 4 CTAs per SM on 148 SMs
 constexpr int RMS_BLOCK = 256;
 
@@ -335,7 +335,7 @@ extern "C" int igi_rms_forward(const float* x, long long rows, int channels, dou
                                double* count, float epsilon, int training, int mode, float* y, void* scratch,
                                void* stream) {
   IGI_REQUIRE(x && running_mean && running_var && count && y, "igi_rms_forward: null pointer");
-  IGI_REQUIRE(channels >= 1 && channels <= RMS_MAX_C, "igi_rms_forward: channels must be 1..16");
+  IGI_REQUIRE(channels >= 1 && channels <= RMS_MAX_C, "igi_rms_forward: channels must be 1..256");
   IGI_REQUIRE(rows >= 0 && mode >= 0 && mode <= 2, "igi_rms_forward: bad rows / mode");
   IGI_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "igi_rms_forward: x and y must be 16-byte aligned");
   if (rows == 0) return IGI_OK;

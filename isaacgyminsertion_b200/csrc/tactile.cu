@@ -83,6 +83,12 @@ struct __align__(16) Setup {       // 64 B record
 };
 static_assert(sizeof(Setup) == 64, "setup record must be 64 B");
 
+// Camera-frame vertex normals of the triangle in the same slot of the setup list (written by tac_geom for the
+// triangles it emits): shading reads them with three independent 128-bit loads instead of walking
+// slot -> face -> vertex ids -> normals and rotating the interpolated normal per pixel.
+struct __align__(16) NRec { float n[12]; };   // n[3*v + c] for vertex v = 0..2, n[9..11] unused
+static_assert(sizeof(NRec) == 48, "normal record must be 48 B");
+
 __device__ __forceinline__ bool make_setup(V3 A, V3 B, V3 C, Setup& s) {
   V3 E1{sub(B.x, A.x), sub(B.y, A.y), sub(B.z, A.z)};
   V3 E2{sub(C.x, A.x), sub(C.y, A.y), sub(C.z, A.z)};
@@ -362,6 +368,8 @@ struct GeomArgs {
   const float* depth0;       // (TH,TW)
   float* M_out;              // (F,12)
   Setup* setups;             // (F, kmax)
+  const float* vnorm;        // (nv,3) vertex normals, object frame
+  NRec* nrecs;               // (F, kmax) camera-frame vertex normals of the emitted triangles
   int32_t* counts;           // (F)   surviving triangles (may exceed kmax -> overflow)
   int32_t* bbox;             // (F,4) dirty window x0,y0,x1,y1
   int32_t* worklist;         // (F)
@@ -497,6 +505,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
   const int ncl = min(s_ncl, GEOM_MAX_CL);
   if (tid == 0) { CT_COUNT(16, ncl); CT_COUNT(17, mi.n_cl); }
   Setup* out = a.setups + (size_t)f * a.kmax;
+  NRec* nout = a.nrecs + (size_t)f * a.kmax;
   const float* hz3 = a.hiz + kc.hiz_off[3];
   const int hw3 = kc.hiz_w[3];
   auto emit = [&](Setup& s, int face, int x0, int y0, int x1, int y1) {
@@ -504,7 +513,23 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
     s.tri = (uint32_t)face;
     s.orig = (uint32_t)a.face_orig[face];
     const int slot = atomicAdd(&s_count, 1);
-    if (slot < a.kmax) out[slot] = s;
+    if (slot < a.kmax) {
+      out[slot] = s;
+      // rotate the three vertex normals into the camera frame once per emitted triangle
+      const int vi[3] = {a.faces[3 * face], a.faces[3 * face + 1], a.faces[3 * face + 2]};
+      float r[12];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) {
+        const float nx = __ldg(a.vnorm + 3 * vi[v]), ny = __ldg(a.vnorm + 3 * vi[v] + 1), nz = __ldg(a.vnorm + 3 * vi[v] + 2);
+        r[3 * v + 0] = sM[0] * nx + sM[1] * ny + sM[2] * nz;
+        r[3 * v + 1] = sM[4] * nx + sM[5] * ny + sM[6] * nz;
+        r[3 * v + 2] = sM[8] * nx + sM[9] * ny + sM[10] * nz;
+      }
+      float4* dst = reinterpret_cast<float4*>(nout + slot);
+      dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+      dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+      dst[2] = make_float4(r[8], 0.f, 0.f, 0.f);
+    }
     atomicMin(&s_bb[0], x0); atomicMin(&s_bb[1], y0); atomicMax(&s_bb[2], x1); atomicMax(&s_bb[3], y1);
   };
   // transform + setup + the cheap culls of one face; false = culled
@@ -650,6 +675,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
 struct ContactArgs {
   const float* M;            // (F,12)
   const Setup* setups;
+  const NRec* nrecs;         // (F, kmax) camera-frame vertex normals per setup slot
   const int32_t* counts;
   const int32_t* bbox;
   const int32_t* worklist;
@@ -852,6 +878,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     if (K <= 0) continue;   // listed only to be filled
     if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
     const Setup* list = a.setups + (size_t)f * a.kmax;
+    const NRec* nlist = a.nrecs + (size_t)f * a.kmax;
     // window that can change: union of the triangle boxes, dilated by the blur radius
     const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
     const int wx1 = min(a.bbox[4 * f + 2] + HALO, TW - 1), wy1 = min(a.bbox[4 * f + 3] + HALO, TH - 1);
@@ -1031,22 +1058,21 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             const unsigned long long key = s_z[i];
             const uint32_t low = (uint32_t)key;
             const float t = __uint_as_float((uint32_t)(key >> 32));
-            const Setup s = load_setup(list + (int)((low - 1u) & 0xfffu));
+            const int slot = (int)((low - 1u) & 0xfffu);
+            const Setup s = load_setup(list + slot);
+            const uint4* nq = reinterpret_cast<const uint4*>(nlist + slot);
+            const uint4 na = __ldg(nq), nb = __ldg(nq + 1), nc = __ldg(nq + 2);
             const float dx = s_dxp[px], dy = s_dyp[py];
             const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
             const float es = add(add(e0, e1), e2);
             const float ies = __fdividef(1.0f, es);
             const float l1 = e1 * ies, l2 = e2 * ies;
             const float l0 = 1.0f - l1 - l2;
-            const int i0 = a.faces[3 * s.tri], i1 = a.faces[3 * s.tri + 1], i2 = a.faces[3 * s.tri + 2];
-            float no[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              no[c] = l0 * __ldg(a.vnorm + 3 * i0 + c) + l1 * __ldg(a.vnorm + 3 * i1 + c) + l2 * __ldg(a.vnorm + 3 * i2 + c);
+            // barycentric blend of the camera-frame vertex normals (rotation and blend commute)
             V3 n;
-            n.x = sM[0] * no[0] + sM[1] * no[1] + sM[2] * no[2];
-            n.y = sM[4] * no[0] + sM[5] * no[1] + sM[6] * no[2];
-            n.z = sM[8] * no[0] + sM[9] * no[1] + sM[10] * no[2];
+            n.x = l0 * __uint_as_float(na.x) + l1 * __uint_as_float(na.w) + l2 * __uint_as_float(nb.z);
+            n.y = l0 * __uint_as_float(na.y) + l1 * __uint_as_float(nb.x) + l2 * __uint_as_float(nb.w);
+            n.z = l0 * __uint_as_float(na.z) + l1 * __uint_as_float(nb.y) + l2 * __uint_as_float(nc.x);
             {
               const float r = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
               n.x *= r; n.y *= r; n.z *= r;
@@ -1403,6 +1429,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
               "igi_tactile_render: null mesh pointer");
   IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid && st->hiz,
               "igi_tactile_render: null static pointer");
+  IGI_REQUIRE(sc->normals, "igi_tactile_render: scratch.normals is null ((F,kmax) 48-byte records)");
   IGI_REQUIRE(sc->M && sc->setups && sc->counts && sc->bbox && sc->worklist && sc->counters && sc->kmax > 0 &&
                   sc->kmax <= 4096,
               "igi_tactile_render: bad scratch (kmax must be 1..4096)");
@@ -1438,7 +1465,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
   g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
   g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz; g.depth0 = st->depth0;
-  g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.counts = sc->counts; g.bbox = sc->bbox;
+  g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.vnorm = m->vnorm; g.nrecs = (NRec*)sc->normals; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
   g.fused_fill = (stages & 8) && parts_geom ? 1 : 0;
@@ -1454,7 +1481,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
     IGI_CHECK_LAUNCH("tac_fill");
   }
   ContactArgs ca{};
-  ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.counts = sc->counts; ca.bbox = sc->bbox;
+  ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.nrecs = (const NRec*)sc->normals; ca.counts = sc->counts; ca.bbox = sc->bbox;
   ca.worklist = sc->worklist; ca.work_n = sc->counters; ca.cursor = sc->counters + 1;
   ca.verts = m->verts; ca.vnorm = m->vnorm; ca.faces = m->faces;
   ca.depth0 = st->depth0; ca.hiz = st->hiz; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;

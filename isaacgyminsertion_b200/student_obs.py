@@ -50,7 +50,7 @@ def queue_push(queue, x):
 
 
 class RunningMeanStd:
-    """running_mean_std.py:22-93 for per_channel=False inputs of shape (rows, C), C = insize <= 16."""
+    """running_mean_std.py:22-93 for per_channel=False inputs of shape (rows, C), C = insize <= 256."""
 
     def __init__(self, insize, epsilon=1e-05, per_channel=False, norm_only=False, device="cuda"):
         if per_channel:
@@ -69,7 +69,7 @@ class RunningMeanStd:
         lib = _lib.load()
         nbytes = lib.igi_rms_scratch_bytes(C)
         if nbytes < 0:
-            raise RuntimeError("RunningMeanStd: insize must be 1..16")
+            raise RuntimeError("RunningMeanStd: insize must be 1..256")
         self._scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
 
     def train(self, mode=True):
@@ -148,10 +148,14 @@ class DepthImageProcessor:
         n = ref.shape[0]
         npix = ref[0].numel()
         dev = ref.device
+        # the converted masks must stay referenced until the launch is enqueued: a temporary freed between
+        # two conversions hands the same block of the caching allocator to the next one
+        m_upd, m_seg, m_noise = (_u8(update, n, dev, "update"), _u8(update_seg, n, dev, "update_seg"),
+                                 _u8(seg_noise, n, dev, "seg_noise"))
         rc = lib.igi_cam_image_obs(
             _lib.dptr(depth, torch.float32, "depth"), _lib.dptr(seg, torch.int32, "seg"),
-            _lib.dptr(_u8(update, n, dev, "update")), _lib.dptr(_u8(update_seg, n, dev, "update_seg")),
-            _lib.dptr(_u8(seg_noise, n, dev, "seg_noise")), _c.c_int(n), _c.c_int(npix), _c.c_longlong(self.env0),
+            _lib.dptr(m_upd), _lib.dptr(m_seg),
+            _lib.dptr(m_noise), _c.c_int(n), _c.c_int(npix), _c.c_longlong(self.env0),
             _c.c_double(self.dis_noise), _c.c_double(self.far_clip), _c.c_double(self.near_clip), _c.c_float(flip_prob),
             _c.c_uint64(self.seed), _c.c_uint32(self.step), _lib.dptr(image_buf, torch.float32, "image_buf"),
             _lib.dptr(seg_buf, torch.int32, "seg_buf"), _stream(dev))
@@ -203,8 +207,9 @@ class PointCloudAugmentations:
         if p.stride(2) != 1 or p.stride(1) != 3:
             raise RuntimeError("random_noise: points must be (B, N, 3) with packed rows")
         noise = pcl_noise.reshape(B, 3).to(torch.float32).contiguous()
+        m = _u8(mask, B, p.device, "mask")   # kept referenced until the launch is enqueued
         rc = lib.igi_pcl_noise(_c.c_void_p(p.data_ptr()), _c.c_int64(p.stride(0)), _c.c_int(B), _c.c_int(N),
-                               _lib.dptr(_u8(mask, B, p.device, "mask")), _lib.dptr(noise), _c.c_longlong(self.env0),
+                               _lib.dptr(m), _lib.dptr(noise), _c.c_longlong(self.env0),
                                _c.c_float(self.sigma), _c.c_float(self.noise_clip), _c.c_float(self.const_noise),
                                _c.c_float(noise_prob), _c.c_uint64(self.seed), _c.c_uint32(self.step),
                                _stream(p.device))
