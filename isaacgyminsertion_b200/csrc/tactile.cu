@@ -200,43 +200,54 @@ __device__ __forceinline__ V3 normalize(V3 v) {
   return v;
 }
 
+// single-MUFU approximations (flush-to-zero): the shading result feeds an 8-bit quantiser
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // pyrender mesh.frag (metallic-roughness, spot lights) -> 8-bit UNORM rgb.
 // NCH = 1 when material and lights are colourless (r == g == b), else 3.  Uses the fast
 // reciprocal / rsqrt / exp2-log2 paths: the result feeds an 8-bit quantiser and is compared with
 // the oracle within 1/255.
-template <int NCH>
+// NL = number of lights when known at compile time (the loop unrolls and the light constants become
+// immediate constant-bank operands), 0 = kc.n_lights.
+template <int NCH, int NL>
 __device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
   const float A2_PI = kc.sh_a2 * 0.31830988618379067f;
-  const float ipl = rsqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+  const float ipl = fast_rsqrt(p.x * p.x + p.y * p.y + p.z * p.z);
   const V3 v{-p.x * ipl, -p.y * ipl, -p.z * ipl};
   const float a2 = kc.sh_a2;
   const float nv_raw = n.x * v.x + n.y * v.y + n.z * v.z;
   const float nv = clampf(nv_raw, 0.001f, 1.0f);
-  const float gv = nv + sqrtf(a2 + (1.0f - a2) * (nv * nv));   // 2 nv / gv = Smith term of the view direction
+  const float gv = nv + fast_sqrt(a2 + (1.0f - a2) * (nv * nv));   // 2 nv / gv = Smith term of the view direction
   float col[NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) col[k] = 0.f;
-  for (int i = 0; i < kc.n_lights; ++i) {
+  const int nl_count = NL ? NL : kc.n_lights;
+#pragma unroll
+  for (int i = 0; i < nl_count; ++i) {
     const V3 L{kc.light_pos[i][0] - p.x, kc.light_pos[i][1] - p.y, kc.light_pos[i][2] - p.z};
-    const float il = rsqrtf(L.x * L.x + L.y * L.y + L.z * L.z);
+    const float il = fast_rsqrt(L.x * L.x + L.y * L.y + L.z * L.z);
     const V3 l{L.x * il, L.y * il, L.z * il};
     // half vector h = (l + v)/|l + v| with |l + v|^2 = 2 + 2 v.l, so n.h and v.h need no vector h
     const float vl = v.x * l.x + v.y * l.y + v.z * l.z;
-    const float ih = rsqrtf(fmaxf(2.0f + 2.0f * vl, 1e-20f));
+    const float ih = fast_rsqrt(fmaxf(2.0f + 2.0f * vl, 1e-20f));
     const float nl_raw = n.x * l.x + n.y * l.y + n.z * l.z;
     const float nl = clampf(nl_raw, 0.001f, 1.0f);
     const float nh = clampf((nl_raw + nv_raw) * ih, 0.001f, 1.0f);
     const float vh = clampf((vl + 1.0f) * ih, 0.001f, 1.0f);
     const float cd = -(kc.light_dir[i][0] * l.x + kc.light_dir[i][1] * l.y + kc.light_dir[i][2] * l.z);
-    float att = clampf(cd * kc.light_las[i] + kc.light_lao[i], 0.0f, 1.0f);
+    float att = __saturatef(cd * kc.light_las[i] + kc.light_lao[i]);
     att = att * att;
     if (kc.inverse_square) att = att * il * il;
     const float w = 1.0f - vh;
     const float w2 = w * w, fw = w2 * w2 * w;
     // specular = G_l G_v D / (4 nl nv) with G_x = 2 x / g_x  ->  D / (g_l g_v)
-    const float gl = nl + sqrtf(a2 + (1.0f - a2) * (nl * nl));
+    const float gl = nl + fast_sqrt(a2 + (1.0f - a2) * (nl * nl));
     const float f = (nh * a2 - nh) * nh + 1.0f;
-    const float sp = __fdividef(A2_PI, f * f * gl * gv);
+    const float sp = A2_PI * fast_rcp(f * f * gl * gv);
     const float na = nl * att;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -246,13 +257,13 @@ __device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
   }
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
-    const float o = clampf(__powf(col[k], 1.0f / 2.2f), 0.0f, 1.0f);
-    rgb[k] = (uint8_t)floorf(o * 255.0f + 0.5f);
+    const float o = __saturatef(fast_ex2(fast_lg2(col[k]) * (1.0f / 2.2f)));
+    rgb[k] = (uint8_t)(o * 255.0f + 0.5f);
   }
   if (NCH == 1) rgb[1] = rgb[2] = rgb[0];
 }
 __device__ __forceinline__ void shade(V3 p, V3 n, uint8_t* rgb) {
-  if (kc.gray) shade_t<1>(p, n, rgb); else shade_t<3>(p, n, rgb);
+  if (kc.gray) shade_t<1, 0>(p, n, rgb); else shade_t<3, 0>(p, n, rgb);
 }
 
 // ---- K0: static gel -------------------------------------------------------------------
@@ -423,7 +434,10 @@ constexpr int GEOM_MAX_CL = 512;
 constexpr int GEOM_ROUND = 256;        // faces prepared per round (2 per thread); survivors are queued in shared memory
 constexpr int GEOM_WARPS = GEOM_BLOCK / 32;
 
-__global__ void __launch_bounds__(GEOM_BLOCK) tac_geom(GeomArgs a) {
+#ifndef GEOM_MIN_CTAS
+#define GEOM_MIN_CTAS 9   // 56 registers: 9 CTAs per SM (no bound: 88 regs, 5 CTAs, 0.82 ms; 8: 0.68 ms; 9: 0.65 ms)
+#endif
+__global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a) {
   __shared__ float sM[12];
   __shared__ int s_cl[GEOM_MAX_CL];
   __shared__ __align__(16) Setup s_q[GEOM_ROUND];   // survivors of the cheap culls of this round
@@ -710,6 +724,18 @@ struct ContactArgs {
 #ifndef CT_ZERO_BYTES
 #define CT_ZERO_BYTES 4096
 #endif
+#ifndef CT_ZINIT_ROWS
+#define CT_ZINIT_ROWS 0
+#endif
+#ifndef CT_ZERO_PLAIN
+#define CT_ZERO_PLAIN 0   // 1: tac_contact zeroes gel_depth with plain streaming stores instead of bulk copies
+#endif
+#ifndef CT_DYN
+#define CT_DYN 1      // 1: warps fetch their raster / shade batches from shared counters instead of a fixed stride
+#endif
+#ifndef CT_SHADE_UNROLL
+#define CT_SHADE_UNROLL 0
+#endif
 constexpr int CT_BLOCK = CT_BLOCK_N;
 constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
 static_assert(CT_CHUNK % CT_BLOCK_N == 0, "CT_CHUNK must be a multiple of the block size");
@@ -811,6 +837,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   __shared__ int s_wsum[CT_BLOCK / 32];
   __shared__ float sM[12];
   __shared__ int s_hits, s_frame, s_next;
+  __shared__ int s_rctr, s_sctr;   // CT_DYN: next raster item / next region pixel to hand out
   __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows)
   __shared__ int s_sb[4];  // bounds of the hit pixels of the current sub-window's region
   __shared__ unsigned short s_q[CT_BLOCK / 32][64];  // per-warp queue of hit pixels waiting to be shaded
@@ -823,12 +850,14 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   for (int i = tid; i < 511; i += CT_BLOCK) s_rb[i] = (double)(i - 255) / 255.0 + 0.5;
   for (int i = tid; i < CT_ZERO_BYTES / 4; i += CT_BLOCK) s_zero[i] = 0.0f;
   igi_fence_proxy_async();   // the zeros must be visible to the bulk-copy (async) proxy
+  const bool three_lights = kc.n_lights == 3;   // the allsight yaml's light count: unrolled shading path
+  (void)three_lights;
   const float span_x0 = k_dxp[0], span_kx = (float)(TW - 1) / (k_dxp[TW - 1] - k_dxp[0]);
   // gel_depth = 0 of one frame (200 704 B of zeros): a few lanes of every warp hand 4 KB pieces of the zero
   // buffer to the bulk-copy engine (shared -> global), which costs this issue-bound kernel no store
   // instructions.  Every thread commits one (possibly empty) bulk group per call.
   auto zero_fill_async = [&](int frame) {
-    if ((a.fill.parts & 2) && a.fill.gel_depth && frame >= 0) {
+    if (!CT_ZERO_PLAIN && (a.fill.parts & 2) && a.fill.gel_depth && frame >= 0) {
       constexpr int NB = TW * TH * 4 / CT_ZERO_BYTES;
       static_assert(NB * CT_ZERO_BYTES == TW * TH * 4, "zero buffer must divide the gel_depth frame");
       constexpr int PER_WARP = (NB + NW - 1) / NW;
@@ -870,9 +899,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     // Fused fill: the other parts of the frame's no-contact result that tac_geom left to this kernel go out
     // with plain stores while the raster / shading work of the frame runs; the barriers below order them
     // before the rewrite of the changed box.
-    if (a.fill.parts & ~2) {
+    if (a.fill.parts & (CT_ZERO_PLAIN ? 7 : ~2)) {
       FillArgs fa = a.fill;
-      fa.parts &= ~2;
+      if (!CT_ZERO_PLAIN) fa.parts &= ~2;
       fill_frame(fa, f, tid, CT_BLOCK);
     }
     if (K <= 0) continue;   // listed only to be filled
@@ -902,6 +931,20 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
         const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
         __syncthreads();
+#if CT_ZINIT_ROWS
+        // --- z-buffer starts as the gel: a warp owns region rows warp, warp + NW, ...; no index division
+        for (int ry = warp; ry < RH; ry += NW) {
+          const int py = ry0 + ry;
+          const bool row_in = py >= cy0 && py <= cy1;
+          const float* drow = a.depth0 + py * TW + rx0;
+          unsigned long long* zrow = s_z + ry * RW;
+          for (int rx = lane; rx < RW; rx += 32) {
+            const int px = rx0 + rx;
+            const float d0 = (row_in && px >= cx0 && px <= cx1) ? __ldg(drow + rx) : 0.0f;
+            zrow[rx] = d0 != 0.0f ? (unsigned long long)__float_as_uint(d0) << 32 : ZEMPTY;
+          }
+        }
+#else
         // --- z-buffer starts as the gel (flattened over the region, 4 independent loads in flight)
         {
           const int npx = RW * RH;
@@ -924,7 +967,8 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
           }
         }
-        if (tid == 0) { s_hits = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
+#endif
+        if (tid == 0) { s_hits = 0; s_sctr = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
         CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
@@ -965,10 +1009,19 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             s_off[tid * (CT_CHUNK / CT_BLOCK) + j] = base;
             base += rows[j];
           }
+          if (tid == 0) s_rctr = 0;
           __syncthreads();
           CT_T(2);
           if (tid == 0) { CT_COUNT(9, total); CT_COUNT(12, 1); CT_COUNT(13, RW * RH); CT_COUNT(14, kn); }
+#if CT_DYN
+          for (;;) {
+            int i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&s_rctr, 32);
+            i0 = __shfl_sync(0xffffffffu, i0, 0);
+            if (i0 >= total) break;
+#else
           for (int i0 = warp * 32; i0 < total; i0 += CT_BLOCK) {
+#endif
             const int i = i0 + lane;
             int k = 0, py = 0, xlo = 0, xhi = -1, exact = 1;
             Setup s;
@@ -1079,7 +1132,11 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
             V3 pp{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
-            shade_t<NCH>(pp, n, rgb);
+#if CT_SHADE_UNROLL
+            if (three_lights) shade_t<NCH, 3>(pp, n, rgb); else shade_t<NCH, 0>(pp, n, rgb);
+#else
+            shade_t<NCH, 0>(pp, n, rgb);
+#endif
             const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
             // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
             if (px >= tx && px <= ix1 && py >= ty && py <= iy1)
@@ -1089,7 +1146,15 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             hx0 = min(hx0, px); hx1 = max(hx1, px); hy0 = min(hy0, py); hy1 = max(hy1, py);
             CT_COUNT(11, 1);
           };
+#if CT_DYN
+          for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_sctr, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= npx) break;
+#else
           for (int base = warp * 32; base < npx; base += CT_BLOCK) {
+#endif
             const int i = base + lane;
             bool hit = false;
             if (i < npx) {
