@@ -285,6 +285,35 @@ int igi_seg_valid_mask(const float* seg, const float* img, long long n, float ob
 int igi_queue_push(float* queue, const void* x, int x_is_int32, int64_t x_stride, int n_envs, int hist_len,
                    long long row_len, void* stream);
 
+/* ----------------------------------------------------------------------------
+ * (L) trajectory logger buffers: device side of DataLoggerSim
+ * (algo/ppo/experience.py:352-490) as used by SimLogger.log_trajectory_data (:634-746) for the
+ * observation rows this library produces (tactile (3,2048), img, seg) and any other (n_envs, L) row.
+ * -------------------------------------------------------------------------- */
+
+/* L1  log[e, counter[e], :] = float(x[e, :]).
+ * Replaces: `self.log_data[key][self.env_ids, self.env_step_counter, ...] = value...` experience.py:426-434
+ *   log (n_envs, episode_len, row_len) f32 (128-bit stores when row_len % 4 == 0); x row e at x + e*x_stride
+ *   elements, f32 or (x_is_int32) i32; x NULL logs zeros (a None value, :430-431); counter (n_envs) i64.
+ *   A counter outside [0, episode_len) sets *overflow = 1 and skips the row (the reference raises). */
+int igi_traj_append(float* log, const void* x, int x_is_int32, int64_t x_stride, const long long* counter, int n_envs,
+                    int episode_len, long long row_len, int32_t* overflow, void* stream);
+
+/* L2  done_log[e, counter[e]] = done[e]; counter[e] += 1; done_ids[0..*n_done) = envs with done set, env order.
+ * Replaces: experience.py:436-445.  done_log rows of done_pitch >= episode_len bytes; done (n_envs) u8 or NULL
+ * (none); done_ids (n_envs) i32; n_done (1) i32. */
+int igi_traj_step(uint8_t* done_log, int done_pitch, const uint8_t* done, long long* counter, int n_envs, int episode_len,
+                  int32_t* done_ids, int32_t* n_done, int32_t* overflow, void* stream);
+
+/* L3  staging[j, :] = buf[ids[j], :] for j < min(*n_ids, max_ids); zero_after != 0 then clears buf[ids[j], :]
+ *     (staging NULL: clear only).  Rows of row_bytes (multiple of 4; 128-bit copies when a multiple of 16) bytes.
+ * Replaces: the per-env `.clone().cpu()` of experience.py:448-455 and _reset_buffers :417-420. */
+int igi_traj_gather(void* buf, const int32_t* ids, const int32_t* n_ids, int max_ids, long long row_bytes, void* staging,
+                    int zero_after, void* stream);
+
+/* counter[ids[j]] = 0 for j < min(*n_ids, max_ids)   (_reset_buffers, experience.py:420). */
+int igi_traj_reset_counters(long long* counter, const int32_t* ids, const int32_t* n_ids, int max_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,12 +52,16 @@ class PointCloudAugmentations:
 class FactoryTaskInsertionTactileObs:
     def __init__(self, num_envs, gym, mesh_ids, bg_ids=None, device="cuda", num_points=400, num_points_socket=400,
                  tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=2048,
-                 strict_rng=True, pcl_noise_enabled=False, overlap_streams=True):
+                 strict_rng=True, pcl_noise_enabled=False, overlap_streams=True, include_all_pcl=False,
+                 total_points=2048):
         self.device = torch.device(device)
         self.num_envs = num_envs
         self.fingertips = ["finger_1_3", "finger_2_3", "finger_3_3"]   # factory_env_insertion.py:748
         self.num_points, self.num_points_socket = num_points, num_points_socket
-        self.pcl_floats = (num_points + num_points_socket) * 3
+        # pcl row = [plug | socket | all-scene] (pcl_components order, factory_task_insertion.py:1014-1027);
+        # include_all_pcl / total_points: FactoryTaskInsertionTactile.yaml:118,124 (off in the shipped config)
+        self.include_all_pcl, self.total_points = bool(include_all_pcl), int(total_points)
+        self.pcl_floats = (num_points + num_points_socket + (self.total_points if self.include_all_pcl else 0)) * 3
         self.sampler = sampler
         self.strict_rng = strict_rng
         self.pcl_noise_enabled = pcl_noise_enabled   # RNG-defined augmentation
@@ -78,6 +82,8 @@ class FactoryTaskInsertionTactileObs:
         self.socket_pcl = (self._both_pts[:, 1] if self._both_pts is not None else
                            torch.zeros((N, num_points_socket, 3), dtype=torch.float32, device=dev))
         self.got_socket = torch.zeros((N, 1), dtype=torch.int32, device=dev)
+        self._all_pts = (torch.zeros((N, self.total_points, 3), dtype=torch.float32, device=dev)
+                         if self.include_all_pcl else None)
         self._socket_pending = True        # host mirror of `not self.got_socket.all()` (no sync)
         self.pcl_pos_noise = torch.randn(N, 1, 3, device=dev)
         self.rot_pcl_angle = torch.zeros(N, device=dev)
@@ -153,6 +159,16 @@ class FactoryTaskInsertionTactileObs:
         self.seg_buf = torch.where(update_seg[:, None], seg.reshape(N, -1), self.seg_buf)            # :934-940
         gen = self.pcl_generator
         box = filter_pts.box
+        all_pts = None
+        if self.include_all_pcl:                                                                    # :946-954
+            # the whole scene: unmasked depth, same box filter, total_points samples.  The reference draws
+            # this cloud BEFORE the plug and socket clouds, so the index stream is consumed in that order.
+            a_pts, a_cnt, a_any = gen.engine.compact(depth, None, (0,), box, tag="all")
+            self._sample(a_pts, a_cnt, a_any, 0, self.total_points, self._all_pts)
+            all_pts = self._all_pts
+            if self.pcl_noise_enabled:
+                all_pts = torch.where(pcl_noise[:, None, None], self.pcl_process.augment(
+                    all_pts, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), all_pts)
         compute_socket = self._socket_pending
         pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3) if compute_socket else (2,), box)     # :956-959,975
         fused = compute_socket and self.sampler == "fps" and self._both_pts is not None
@@ -176,8 +192,10 @@ class FactoryTaskInsertionTactileObs:
             self.got_socket.masked_fill_(restarted[:, None], 1)      # no boolean-index host sync
             update = update | restarted
             self._socket_pending = False
-        if plug_pts is self._plug_pts and self._both_pts is not None:
-            merged = self._both_pts.view(N, -1)                                                      # :1014-1027
+        if all_pts is not None:
+            merged = torch.cat([plug_pts, self.socket_pcl, all_pts], dim=1).flatten(start_dim=1)     # :1014-1027
+        elif plug_pts is self._plug_pts and self._both_pts is not None:
+            merged = self._both_pts.view(N, -1)
         else:
             merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)
         self.pcl.copy_(torch.where(update[:, None], merged, self.pcl))

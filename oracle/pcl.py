@@ -102,8 +102,11 @@ def masked_depth(depth, seg, seg_id):
     return (depth.flatten(start_dim=1) * (seg.flatten(start_dim=1) == seg_id)).reshape(depth.shape)
 
 
-def pcl_observation(cams, depth, seg, num_points=400, num_points_socket=400):
-    """plug cloud then socket cloud (RNG order of factory_task_insertion.py:961-979), merged (:1014-1027)."""
+def pcl_observation(cams, depth, seg, num_points=400, num_points_socket=400, include_all_pcl=False, total_points=2048):
+    """[all-scene cloud first when include_all_pcl (:946-949)], plug cloud, then socket cloud (RNG order of
+    factory_task_insertion.py:946-979), merged in pcl_components order plug | socket | all (:1014-1027)."""
+    all_pts = get_point_cloud(cams, depth, total_points) if include_all_pcl else None
     plug = get_point_cloud(cams, masked_depth(depth, seg, 2), num_points)
     socket = get_point_cloud(cams, masked_depth(depth, seg, 3), num_points_socket)
-    return torch.cat([plug, socket], dim=1).flatten(start_dim=1)
+    parts = [plug, socket] + ([all_pts] if include_all_pcl else [])
+    return torch.cat(parts, dim=1).flatten(start_dim=1)

@@ -97,6 +97,39 @@ def test_task_observation_functions_match_oracle(built_lib):
     assert float(task.tactile_queue[1].abs().max()) == 0 and int(task.got_socket[4]) == 0 and int(task.got_socket[0]) == 1
 
 
+def test_include_all_pcl_matches_oracle(built_lib):
+    """include_all_pcl (FactoryTaskInsertionTactile.yaml:124): the unmasked scene cloud is drawn FIRST from the
+    torch.randint stream (factory_task_insertion.py:946-949) and appended LAST to the pcl row (:1014-1027)."""
+    from oracle import pcl as opcl
+    n, tp = 5, 256
+    gym, P, depth, seg = _inputs(n, seed=5)
+    task = _task(n, gym, P, sampler="reference", tactile=False, include_all_pcl=True, total_points=tp)
+    _load(task, P, depth, seg)
+    ones = torch.ones(n, dtype=torch.bool, device=DEV)
+    zeros = torch.zeros(n, dtype=torch.bool, device=DEV)
+    torch.manual_seed(5)
+    task.update_external_cam(ones, ones, ones, zeros, zeros)
+    torch.manual_seed(5)
+    want = opcl.pcl_observation(opcl.build_cameras(gym), torch.from_numpy(depth), torch.from_numpy(seg),
+                                include_all_pcl=True, total_points=tp)
+    assert task.pcl.shape == (n, (400 + 400 + tp) * 3)
+    tol = 1e-5 * float(np.abs(gym.origins).max() + 1.0)
+    np.testing.assert_allclose(task.pcl.cpu().numpy(), want.numpy(), rtol=1e-5, atol=tol)
+    # FPS sampler on the same clouds: every all-scene sample is one of the env's box-filtered scene points
+    task2 = _task(n, gym, P, sampler="fps", tactile=False, include_all_pcl=True, total_points=tp)
+    _load(task2, P, depth, seg)
+    task2.update_external_cam(ones, ones, ones, zeros, zeros)
+    allc = task2.pcl.view(n, -1, 3)[:, 800:].cpu().numpy()
+    cams = opcl.build_cameras(gym)
+    scene = opcl.get_ptd(cams, torch.from_numpy(depth), opcl.filter_pts)
+    for e in range(n):
+        pool = scene[e].numpy()
+        assert pool.shape[0] > tp
+        d = np.abs(allc[e][:, None, :] - pool[None, :, :]).max(-1).min(-1)
+        assert d.max() <= tol
+        assert len(np.unique(allc[e], axis=0)) == tp      # FPS never repeats while unpicked points remain
+
+
 def test_multi_region_path_is_identical(built_lib):
     """Small region budgets force the contact kernel to cut every window into several regions (obs then
     comes from the global-memory path); results must not depend on the cut."""
