@@ -429,6 +429,9 @@ __device__ unsigned long long g_ct_prof[32];
 #define CT_COUNT(slot, v) do { } while (0)
 #endif
 
+#ifndef CT_PDL
+#define CT_PDL 0      // 1: tac_contact launched with programmatic stream serialization behind tac_geom (measured: path -0.01 ms, whole step +0.08 ms: the early-resident CTAs keep the side-stream pcl kernels off the SMs)
+#endif
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
 constexpr int GEOM_ROUND = 256;        // faces prepared per round (2 per thread); survivors are queued in shared memory
@@ -450,6 +453,11 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a
   const int f = blockIdx.x;
   const int env = f / a.sensors_per_env;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if CT_PDL
+  // Once every CTA of this grid has STARTED, tac_contact's CTAs may become resident on the SMs the last wave
+  // leaves idle and run their table prologue; they wait for this grid's completion before reading its results.
+  cudaTriggerProgrammaticLaunchCompletion();
+#endif
   if (a.update && !a.update[env]) {
     if (tid == 0) a.counts[f] = -1;  // frame not rendered this step
     return;
@@ -869,6 +877,11 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     }
     igi_bulk_commit();
   };
+#if CT_PDL
+  // Programmatic dependent launch: everything above touched only constants and shared memory, so it ran while
+  // tac_geom's last CTAs were still draining; from here on its results (worklist, setups, fill) are needed.
+  cudaGridDependencySynchronize();
+#endif
   // Work items are fetched ONE FRAME AHEAD: the zero fill of the next frame is issued when the current
   // frame starts, so it has a whole frame time to land before that frame's first gel_depth write.
   if (tid == 0) {
@@ -1571,8 +1584,25 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
       IGI_CUDA(cudaFuncSetAttribute(tac_contact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rgb));
       attr_set = true;
     }
+#if CT_PDL
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(g_gray ? min(F, sms * CT_CTAS) : min(F, sms)));
+      cfg.blockDim = dim3(CT_BLOCK);
+      cfg.dynamicSmemBytes = g_gray ? smem_gray : smem_rgb;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (g_gray) IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<1>, ca));
+      else IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<3>, ca));
+    }
+#else
     if (g_gray) tac_contact<1><<<min(F, sms * CT_CTAS), CT_BLOCK, smem_gray, s>>>(ca);
     else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(ca);
+#endif
     IGI_CHECK_LAUNCH("tac_contact");
   }
   return IGI_OK;
