@@ -1,6 +1,7 @@
 """Stages next to the hot path, same names and signatures as the reference's:
 
   RunningMeanStd         algo/models/running_mean_std.py:22-93      (student normaliser)
+  TactileTransform       algo/models/transformer/utils.py:131-156   (batched, identity-size short cut)
   process_obs            algo/ext_adapt/ext_adapt.py:383-435        (ExtrinsicAdapt.process_obs)
   DepthImageProcessor    tasks/factory_tactile/factory_utils.py:12-72
   PointCloudAugmentations.random_noise   factory_utils.py:83-100
@@ -132,6 +133,27 @@ def process_obs(obs, pcl_mean_std=None, stud_obs_mean_std=None, obj_id=2, socket
     if student_obs is not None and stud_obs_mean_std is not None:
         student_obs = stud_obs_mean_std(student_obs)
     return {"student_obs": student_obs, "tactile": tactile, "img": img, "seg": seg, "pcl": pcl}
+
+
+class TactileTransform:
+    """algo/models/transformer/utils.py:131-156 without the per-image Python loop (3*N*T iterations per step).
+
+    The student's eval transform is Resize((w, h), bilinear) -> CenterCrop((cw, ch)) (`define_tactile_transforms`,
+    utils.py:217-274).  Both are pure per-image functions, so applying them once to the flattened
+    (B*T*F, C, H, W) batch gives the same pixels as the reference's loop; at the shipped sizes (32 x 64 in,
+    32 x 64 out; FactoryTaskInsertionTactile.yaml:39-46) they are the identity and nothing is launched at all.
+    `identity_size=(H, W)`: the (resize == crop) size for which the transform may be skipped."""
+
+    def __init__(self, tactile_transform=None, identity_size=None):
+        self.tactile_transform = tactile_transform
+        self.identity_size = tuple(identity_size) if identity_size is not None else None
+
+    def __call__(self, tac_input):
+        B, T, F, C, H, W = tac_input.shape
+        if self.tactile_transform is None or (H, W) == self.identity_size:
+            return tac_input
+        out = self.tactile_transform(tac_input.reshape(-1, C, H, W))
+        return out.view(B, T, F, C, *out.shape[2:])
 
 
 class DepthImageProcessor:

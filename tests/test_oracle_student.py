@@ -93,3 +93,27 @@ def test_queue_push():
     x = torch.full((2, 4), -1.0)
     ost.queue_push(q, x)
     assert torch.equal(q[:, 0], x) and torch.equal(q[:, 1:], q0[:, :-1])
+
+
+def test_tactile_transform_equals_per_image_loop():
+    """The batched TactileTransform == the reference's per-image loop (utils.py:140-156) for its eval transform
+    (Resize bilinear -> CenterCrop, utils.py:217-274), and is skipped at the identity size."""
+    from torchvision import transforms
+    from isaacgyminsertion_b200.student_obs import TactileTransform
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((2, 2, 3, 1, 32, 64), generator=g)
+
+    def loop(tf, tac):                       # the reference's __call__
+        B, T, F, C, H, W = tac.shape
+        flat = tac.view(-1, C, H, W)
+        out = torch.stack([tf(flat[i]) for i in range(flat.shape[0])])
+        return out.view(B, T, F, C, *out.shape[2:])
+    ident = torch.nn.Sequential(transforms.Resize((32, 64), interpolation=transforms.InterpolationMode.BILINEAR),
+                                transforms.CenterCrop((32, 64)))
+    assert torch.equal(loop(ident, x), x)                                     # identity at the shipped sizes
+    assert TactileTransform(ident, identity_size=(32, 64))(x) is x
+    assert torch.equal(TactileTransform(ident)(x), x)
+    small = torch.nn.Sequential(transforms.Resize((16, 32), interpolation=transforms.InterpolationMode.BILINEAR),
+                                transforms.CenterCrop((12, 24)))
+    got, want = TactileTransform(small)(x), loop(small, x)
+    assert got.shape == (2, 2, 3, 1, 12, 24) and torch.allclose(got, want, atol=1e-6)
