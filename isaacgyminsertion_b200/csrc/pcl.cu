@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
 // Inner loop, branch free: a point that can never be picked (|p|^2 <= 1e-3, or beyond n) keeps a running
 // minimum of -1, distances are >= 0, so a float max over min(d, temp) ignores it; the winner among equal
 // distances is then the largest tie key among the points whose minimum equals the max.
-constexpr int FW_WARPS = 4, FW_MAXN = 384, FW_COOP_MAXN = 1024, FW_COOP_PPL = FW_COOP_MAXN / (FW_WARPS * 32);
+// FW_MAXN: largest task one warp runs alone.  Above it the four warps of the CTA share the task: the total work per
+// pick is about the same (4 warps x n/128 points vs 1 warp x n/32), but the chain of dependent picks - which is what
+// the few longest tasks of a step cost - gets 3-4x shorter.
+constexpr int FW_WARPS = 4, FW_MAXN = 256, FW_COOP_MAXN = 1024, FW_COOP_PPL = FW_COOP_MAXN / (FW_WARPS * 32);
 
 __device__ __forceinline__ uint32_t fps_tie_key(int k, int lg, uint32_t bmask) {
   const uint32_t rev = lg ? bitrev_n((uint32_t)k & bmask, lg) : 0u;
@@ -483,17 +486,38 @@ __device__ __forceinline__ uint32_t fps_tie(const float* temp, const uint32_t* l
 // The m-1 dependent picks of one warp-resident task.  Fills sel[0..m).  Once the winning distance is 0
 // (all points already picked, or only duplicates left) or nothing is a candidate, the minima cannot
 // change any more and every later pick repeats the same index, so the loop stops there.
-template <int PPL>
+// REG: the lane's points live in registers for the whole task (3 * PPL registers), so a pick reads shared
+// memory only for the coordinates of the point picked last; used while PPL is small enough for the 64-register cap.
+template <int PPL, bool REG>
 __device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy, const float* sz, int n, int m,
                                                int lane, unsigned short* sel) {
   float temp[PPL];
   uint32_t lokey[PPL];
   fps_init_state<PPL>(sx, sy, sz, n, lane, 32, temp, lokey);
+  float px[REG ? PPL : 1], py[REG ? PPL : 1], pz[REG ? PPL : 1];
+  if (REG) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) { px[i] = sx[lane + 32 * i]; py[i] = sy[lane + 32 * i]; pz[i] = sz[lane + 32 * i]; }
+  }
   int old = 0;
   if (lane == 0) sel[0] = 0;
   int j = 1;
   for (; j < m; ++j) {
-    const float best = fps_update<PPL>(sx, sy, sz, old, lane, 32, temp);
+    float best;
+    if (REG) {
+      const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+      best = -1.0f;
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d2 = fminf(d, temp[i]);
+        temp[i] = d2;
+        best = fmaxf(best, d2);
+      }
+    } else {
+      best = fps_update<PPL>(sx, sy, sz, old, lane, 32, temp);
+    }
     const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));   // floats >= 0 order as ints; -1 < 0
     const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
     old = (wb < 0) ? 0 : (int)((~wlo) & 0xffffu);
@@ -516,24 +540,22 @@ struct FpsTaskArgs {
 };
 constexpr int FW_PLANE = FW_WARPS * FW_MAXN > FW_COOP_MAXN ? FW_WARPS * FW_MAXN : FW_COOP_MAXN;
 
-// A task of FW_MAXN+1 .. FW_COOP_MAXN points, run by all warps of the CTA (one barrier per pick).
-__device__ __forceinline__ void fps_coop_task(const FpsTaskArgs& a, int task, int n, float* s_p, int2 (*s_cand)[FW_WARPS]) {
+// A task of FW_MAXN+1 .. FW_COOP_MAXN points, run by all warps of the CTA (one barrier per pick); PPL points per
+// thread, held in registers.
+template <int PPL>
+__device__ __forceinline__ void fps_coop_picks(const FpsTaskArgs& a, int task, int n, const float* sx, const float* sy,
+                                               const float* sz, int2 (*s_cand)[FW_WARPS]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m = a.m;
-  float* sx = s_p;
-  float* sy = sx + FW_PLANE;
-  float* sz = sy + FW_PLANE;
-  __syncthreads();
-  const float* src = a.pts + (size_t)task * a.task_stride;
-  for (int i = tid; i < 3 * n; i += FW_WARPS * 32) {
-    const int k = i / 3, c = i - 3 * k;
-    s_p[c * FW_PLANE + k] = src[i];
+  float temp[PPL];
+  uint32_t lokey[PPL];
+  fps_init_state<PPL>(sx, sy, sz, n, tid, FW_WARPS * 32, temp, lokey);
+  float px[PPL], py[PPL], pz[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const int k = tid + FW_WARPS * 32 * i;
+    px[i] = sx[k]; py[i] = sy[k]; pz[i] = sz[k];
   }
-  for (int k = n + tid; k < FW_COOP_MAXN; k += FW_WARPS * 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
-  __syncthreads();
-  float temp[FW_COOP_PPL];
-  uint32_t lokey[FW_COOP_PPL];
-  fps_init_state<FW_COOP_PPL>(sx, sy, sz, n, tid, FW_WARPS * 32, temp, lokey);
   float* dst = a.out_pts ? a.out_pts + (size_t)task * a.out_stride : nullptr;
   int32_t* idst = a.out_idx ? a.out_idx + (size_t)task * m : nullptr;
   int old = 0;
@@ -543,9 +565,18 @@ __device__ __forceinline__ void fps_coop_task(const FpsTaskArgs& a, int task, in
   }
   int j = 1;
   for (; j < m; ++j) {
-    const float best = fps_update<FW_COOP_PPL>(sx, sy, sz, old, tid, FW_WARPS * 32, temp);
+    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    float best = -1.0f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float d2 = fminf(d, temp[i]);
+      temp[i] = d2;
+      best = fmaxf(best, d2);
+    }
     const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));
-    const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<FW_COOP_PPL>(temp, lokey, wb));
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
     if (lane == 0) s_cand[j & 1][warp] = make_int2(wb, (int)wlo);
     __syncthreads();
     int fb = -2;
@@ -565,6 +596,30 @@ __device__ __forceinline__ void fps_coop_task(const FpsTaskArgs& a, int task, in
   for (int i = j + tid; i < m; i += FW_WARPS * 32) {
     if (idst) idst[i] = old;
     if (dst) { dst[i * 3 + 0] = sx[old]; dst[i * 3 + 1] = sy[old]; dst[i * 3 + 2] = sz[old]; }
+  }
+}
+
+__device__ __forceinline__ void fps_coop_task(const FpsTaskArgs& a, int task, int n, float* s_p, int2 (*s_cand)[FW_WARPS]) {
+  const int tid = threadIdx.x;
+  float* sx = s_p;
+  float* sy = sx + FW_PLANE;
+  float* sz = sy + FW_PLANE;
+  __syncthreads();
+  const float* src = a.pts + (size_t)task * a.task_stride;
+  for (int i = tid; i < 3 * n; i += FW_WARPS * 32) {
+    const int k = i / 3, c = i - 3 * k;
+    s_p[c * FW_PLANE + k] = src[i];
+  }
+  int ppl = (n + FW_WARPS * 32 - 1) / (FW_WARPS * 32);   // 3 .. 8 for n in (256, 1024]
+  ppl = ppl < 3 ? 3 : (ppl > 6 ? FW_COOP_PPL : ppl);       // the instantiated sizes
+  for (int k = n + tid; k < ppl * FW_WARPS * 32; k += FW_WARPS * 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
+  __syncthreads();
+  switch (ppl) {
+    case 3: fps_coop_picks<3>(a, task, n, sx, sy, sz, s_cand); break;
+    case 4: fps_coop_picks<4>(a, task, n, sx, sy, sz, s_cand); break;
+    case 5: fps_coop_picks<5>(a, task, n, sx, sy, sz, s_cand); break;
+    case 6: fps_coop_picks<6>(a, task, n, sx, sy, sz, s_cand); break;
+    default: fps_coop_picks<FW_COOP_PPL>(a, task, n, sx, sy, sz, s_cand); break;
   }
 }
 
@@ -593,12 +648,18 @@ __device__ __forceinline__ void fps_warp_task(const FpsTaskArgs& a, int task, in
     const int k = i / 3, c = i - 3 * k;
     sx[c * FW_PLANE + k] = src[i];
   }
-  const int npad = n <= 128 ? 128 : (n <= 256 ? 256 : FW_MAXN);
-  for (int k = n + lane; k < npad; k += 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
+  // points per lane in steps of one up to 8 (the per-pick work is proportional to it), then 10 and 12
+  const int ppl = n <= 128 ? 4 : (n + 31) >> 5;   // 4 .. FW_MAXN / 32
+  for (int k = n + lane; k < 32 * ppl; k += 32) { sx[k] = 0.f; sy[k] = 0.f; sz[k] = 0.f; }
   __syncwarp();
-  if (n <= 128) fps_warp_picks<4>(sx, sy, sz, n, m, lane, sel);
-  else if (n <= 256) fps_warp_picks<8>(sx, sy, sz, n, m, lane, sel);
-  else fps_warp_picks<FW_MAXN / 32>(sx, sy, sz, n, m, lane, sel);
+  switch (ppl) {
+    case 4: fps_warp_picks<4, true>(sx, sy, sz, n, m, lane, sel); break;
+    case 5: fps_warp_picks<5, true>(sx, sy, sz, n, m, lane, sel); break;
+    case 6: fps_warp_picks<6, true>(sx, sy, sz, n, m, lane, sel); break;
+    case 7: fps_warp_picks<7, true>(sx, sy, sz, n, m, lane, sel); break;
+    default: fps_warp_picks<FW_MAXN / 32, true>(sx, sy, sz, n, m, lane, sel); break;
+  }
+  static_assert(FW_MAXN / 32 == 8, "the switch above covers 4 .. 8 points per lane");
   __syncwarp();
   for (int i = lane; i < m; i += 32) {
     const int k = sel[i];

@@ -140,7 +140,7 @@ def test_fps_balanced_mixed_sizes(built_lib):
     import ctypes as c
     from isaacgyminsertion_b200 import _lib
     lib = _lib.load()
-    sizes = [0, 1, 5, 100, 128, 129, 256, 257, 384, 385, 700, 1024, 1025, 3000, 17, 400, 64, 383, 1023, 2]
+    sizes = [0, 1, 5, 100, 128, 129, 160, 161, 224, 256, 257, 384, 385, 512, 513, 640, 700, 768, 769, 1024, 1025, 3000, 17, 400, 64, 383, 1023, 2, 96]
     rng = np.random.default_rng(11)
     T, cap, m = 3 * len(sizes), 3000, 400
     counts = np.array([sizes[(7 * t) % len(sizes)] for t in range(T)], dtype=np.int32)
@@ -160,7 +160,7 @@ def test_fps_balanced_mixed_sizes(built_lib):
     sched = scratch[:5].cpu().numpy()
     live = (counts > 0) & (anyf != 0)
     assert sched[4] == int(((counts > 1024) & live).sum())
-    assert sched[1] == T - sched[4] and sched[0] == int(((counts > 384) & (counts <= 1024) & live).sum())
+    assert sched[1] == T - sched[4] and sched[0] == int(((counts > 256) & (counts <= 1024) & live).sum())   # FW_MAXN = 256
     order = scratch[8:8 + sched[1]].cpu().numpy()
     assert len(set(order.tolist())) == sched[1]          # every listed task exactly once
     key = np.where(live, counts, 0)[order]
