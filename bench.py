@@ -453,6 +453,8 @@ def main():
         copy_bytes_out = h_out.numel() * h_out.element_size()
 
         from isaacgyminsertion_b200.pipeline import HostObsPipeline
+        from isaacgyminsertion_b200 import pipeline as _pl
+        E2E_DEPTH = _pl.SLOTS - 1
         pipe = HostObsPipeline(task, sampler_socket_every_step=True)
         copy_bytes_in, copy_bytes_out = pipe.h2d_bytes, pipe.d2h_bytes
         handles = []
@@ -461,8 +463,8 @@ def main():
             # host buffers in, host result out, every step: upload / kernels / download of
             # neighbouring steps overlap on three streams (isaacgyminsertion_b200.pipeline)
             handles.append(pipe.step(h_fpos, h_fquat, h_ppos, h_pquat, h_depth, h_seg))
-            if len(handles) > 2:
-                handles.pop(0).wait()      # the learner reads step i-2's observations
+            if len(handles) > E2E_DEPTH:
+                handles.pop(0).wait()      # the learner reads the observations of step i - (SLOTS - 1)
             if world > 1:
                 obs_gather(i)
         # the same K steps as the resident leg; the timed region includes filling and draining the 3-stage

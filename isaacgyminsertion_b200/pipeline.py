@@ -13,10 +13,12 @@ D2H copy of step i-1 overlap the kernels of step i.  A result stays valid until 
 have been submitted; host input buffers must not be modified until the step's `.wait()` returned
 (or `uploaded.synchronize()`).
 """
+import os
+
 import torch
 
 
-SLOTS = 3
+SLOTS = int(os.environ.get("IGI_PIPE_SLOTS", "3"))   # ring depth (>= 2); 3 = one step uploading, one computing, one downloading
 
 
 class PendingObs:
