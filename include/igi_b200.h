@@ -104,6 +104,10 @@ int igi_fps_balanced(const float* pts, int64_t task_stride, const int32_t* count
                      int64_t count_stride, int n_tasks, int m, float* out_pts, int64_t out_stride,
                      int32_t* out_idx, int32_t* scratch, void* stream);
 
+/* Tasks of 1025..8192 points run on thread-block clusters (4 CTAs x 256 threads, candidates exchanged through
+ * distributed shared memory); enabled = 0 sends them to the one-CTA kernel instead (same results; for A/B timing). */
+int igi_fps_set_cluster(int enabled);
+
 /* --------------------------------------------------------------------------
  * (T) allsight tactile renderer
  * -------------------------------------------------------------------------- */

@@ -1,7 +1,11 @@
 // (P) external-camera point-cloud path: K4 unproject/filter/compact, K5A gather, K5B FPS.
 // Entry points are declared in include/igi_b200.h.
+#include <cooperative_groups.h>
+
 #include "igi_common.cuh"
 #include "../../include/igi_b200.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -322,9 +326,12 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
                                                         const int32_t* count, const int32_t* any,
                                                         int64_t count_stride, int n_fixed, int n_tasks, int m,
                                                         float* out_pts, int64_t out_stride, int32_t* out_idx,
-                                                        int min_n, const int32_t* sched, const int32_t* order) {
+                                                        int min_n, const int32_t* sched, const int32_t* order,
+                                                        int cluster_limit, int cluster_maxn) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ FpsCand s_cand[2][kFpsBlock / 32];
+  // a short list of big tasks belongs to fps_cluster_kernel up to its size limit (same rule there)
+  if (sched && cluster_limit > 0 && sched[4] <= cluster_limit && min_n <= cluster_maxn) min_n = cluster_maxn + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // persistent CTAs stride over the tasks; tasks below min_n belong to fps_warp_kernel / fps_sorted_kernel.
   // With a schedule (igi_fps_balanced) only the tasks fps_order_kernel listed as big are visited.
@@ -694,6 +701,137 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 8) fps_warp_kernel(FpsTaskArgs 
   fps_warp_task(a, task, n, live, s_p, s_sel_all);
 }
 
+// ---- cluster FPS: tasks of FW_COOP_MAXN+1 .. FC_MAXN points ------------------------------------------
+// One thread-block cluster (FC_CL CTAs x FC_BLOCK threads = 1024 threads on FC_CL SMs) per task.  Every
+// thread keeps its PPL points, their running minima and tie keys in registers for the whole task (no
+// shared-memory point arrays at all); per pick each warp reduces its lanes with two REDUX instructions and
+// writes its candidate - distance, tie key and the candidate's coordinates - into the candidate table of
+// EVERY CTA of the cluster through distributed shared memory, one cluster barrier makes the 32 candidates
+// visible, and every warp reduces them again with REDUX, so all 1024 threads leave the barrier knowing the
+// picked point's index and coordinates without another memory round trip.  Same arithmetic and selection rule
+// as the other FPS kernels / oracle/fps.py.
+constexpr int FC_CL = 4, FC_BLOCK = 256, FC_THREADS = FC_CL * FC_BLOCK, FC_MAXPPL = 8, FC_MAXN = FC_MAXPPL * FC_THREADS;
+// Clusters shorten the chain of dependent picks of ONE task (5x at 8-64 tasks of 5184 points) but finish fewer tasks
+// per second than 128-thread CTAs once the machine is full of tasks (measured cross-over between 512 and 4096 tasks).
+constexpr int FC_TASK_LIMIT = 512;
+constexpr int FC_CANDS = FC_THREADS / 32;   // 32 warps in the cluster = one candidate per lane
+static_assert(FC_CANDS == 32, "the second reduction maps one candidate to each lane");
+struct __align__(8) FcCand { int hi; uint32_t lo; float x, y, z; uint32_t pad; };
+
+template <int PPL>
+__device__ __forceinline__ void fps_cluster_picks(cg::cluster_group& cluster, const float* __restrict__ src, int n, int m,
+                                                  float* dst, int32_t* idst, FcCand (*s_cand)[FC_CANDS]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster.block_rank();
+  const int gtid = rank * FC_BLOCK + tid;
+  int lg = 31 - __clz(n);
+  if (lg > 9) lg = 9;
+  const uint32_t bmask = (1u << lg) - 1u;
+  float px[PPL], py[PPL], pz[PPL], temp[PPL];
+  uint32_t lokey[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const int k = gtid + FC_THREADS * i;
+    px[i] = 0.f; py[i] = 0.f; pz[i] = 0.f; temp[i] = -1.0f; lokey[i] = 0u;
+    if (k < n) {
+      px[i] = src[(size_t)k * 3 + 0]; py[i] = src[(size_t)k * 3 + 1]; pz[i] = src[(size_t)k * 3 + 2];
+      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(px[i], px[i]), __fmul_rn(py[i], py[i])), __fmul_rn(pz[i], pz[i]));
+      if (mag > 1e-3f) { temp[i] = 1e10f; lokey[i] = fps_tie_key(k, lg, bmask); }
+    }
+  }
+  const float x0 = src[0], y0 = src[1], z0 = src[2];
+  float x1 = x0, y1 = y0, z1 = z0;   // coordinates of the point picked last
+  int old = 0;
+  if (gtid == 0) {
+    if (idst) idst[0] = 0;
+    if (dst) { dst[0] = x0; dst[1] = y0; dst[2] = z0; }
+  }
+  int j = 1;
+  for (; j < m; ++j) {
+    float best = -1.0f;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float d2 = fminf(d, temp[i]);
+      temp[i] = d2;
+      best = fmaxf(best, d2);
+    }
+    const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));   // floats >= 0 order as ints; -1 < 0
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
+    // coordinates of the warp's candidate: the (unique) slot whose tie key is wlo
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    bool mine = false;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i)
+      if (wlo != 0u && lokey[i] == wlo) { cx = px[i]; cy = py[i]; cz = pz[i]; mine = true; }
+    const unsigned owners = __ballot_sync(0xffffffffu, mine);
+    const int owner = owners ? __ffs(owners) - 1 : 0;
+    cx = __shfl_sync(0xffffffffu, cx, owner); cy = __shfl_sync(0xffffffffu, cy, owner); cz = __shfl_sync(0xffffffffu, cz, owner);
+    if (lane < FC_CL) {   // lane r stores the warp's candidate into CTA r's table
+      FcCand* table = cluster.map_shared_rank(&s_cand[j & 1][0], lane);
+      FcCand c;
+      c.hi = wb; c.lo = wlo; c.x = cx; c.y = cy; c.z = cz; c.pad = 0u;
+      table[rank * (FC_BLOCK / 32) + warp] = c;
+    }
+    cluster.sync();
+    const FcCand c = s_cand[j & 1][lane];
+    const int fb = __reduce_max_sync(0xffffffffu, c.hi);
+    const uint32_t flo = __reduce_max_sync(0xffffffffu, c.hi == fb ? c.lo : 0u);
+    const unsigned winners = __ballot_sync(0xffffffffu, c.hi == fb && c.lo == flo);
+    const int win = __ffs(winners) - 1;
+    if (fb < 0) { old = 0; x1 = x0; y1 = y0; z1 = z0; }
+    else {
+      old = (int)((~flo) & 0xffffu);
+      x1 = __shfl_sync(0xffffffffu, c.x, win); y1 = __shfl_sync(0xffffffffu, c.y, win); z1 = __shfl_sync(0xffffffffu, c.z, win);
+    }
+    if (gtid == 0) {
+      if (idst) idst[j] = old;
+      if (dst) { dst[j * 3 + 0] = x1; dst[j * 3 + 1] = y1; dst[j * 3 + 2] = z1; }
+    }
+    if (fb <= 0) { ++j; break; }   // cluster-uniform: every thread reduced the same table
+  }
+  for (int i = j + gtid; i < m; i += FC_THREADS) {
+    if (idst) idst[i] = old;
+    if (dst) { dst[i * 3 + 0] = x1; dst[i * 3 + 1] = y1; dst[i * 3 + 2] = z1; }
+  }
+}
+
+__global__ void __cluster_dims__(FC_CL, 1, 1) __launch_bounds__(FC_BLOCK)
+    fps_cluster_kernel(FpsTaskArgs a, int min_n, const int32_t* sched, const int32_t* order) {
+  __shared__ FcCand s_cand[2][FC_CANDS];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cid = blockIdx.x / FC_CL, n_clusters = gridDim.x / FC_CL;
+  const int gtid = (int)cluster.block_rank() * FC_BLOCK + threadIdx.x;
+  const int m = a.m;
+  // With a schedule (igi_fps_balanced) only the tasks fps_order_kernel listed as big are visited.
+  const int n_iter = sched ? sched[4] : a.n_tasks;
+  if (sched && n_iter > FC_TASK_LIMIT) return;   // a long list is better served by the one-CTA kernel (uniform exit)
+  for (int it = cid; it < n_iter; it += n_clusters) {
+    const int task = sched ? order[a.n_tasks - 1 - it] : it;
+    const int n = a.count ? a.count[(size_t)task * a.count_stride] : a.n_fixed;
+    if (n < min_n || n > FC_MAXN) continue;   // the resident kernels' / fps_kernel's
+    const bool live = (a.any ? a.any[(size_t)task * a.count_stride] != 0 : true) && n > 0;
+    float* dst = a.out_pts ? a.out_pts + (size_t)task * a.out_stride : nullptr;
+    int32_t* idst = a.out_idx ? a.out_idx + (size_t)task * m : nullptr;
+    if (!live) {
+      for (int i = gtid; i < m; i += FC_THREADS) {
+        if (dst) { dst[i * 3 + 0] = 0.f; dst[i * 3 + 1] = 0.f; dst[i * 3 + 2] = 0.f; }
+        if (idst) idst[i] = 0;
+      }
+      continue;
+    }
+    cluster.sync();   // the previous task's last table has been read by every CTA
+    const float* src = a.pts + (size_t)task * a.task_stride;
+    const int ppl = (n + FC_THREADS - 1) / FC_THREADS;
+    if (ppl <= 2) fps_cluster_picks<2>(cluster, src, n, m, dst, idst, s_cand);
+    else if (ppl <= 4) fps_cluster_picks<4>(cluster, src, n, m, dst, idst, s_cand);
+    else if (ppl <= 6) fps_cluster_picks<6>(cluster, src, n, m, dst, idst, s_cand);
+    else fps_cluster_picks<FC_MAXPPL>(cluster, src, n, m, dst, idst, s_cand);
+  }
+  cluster.sync();   // no CTA leaves while a peer may still write into its table
+}
+
 // ---- size-ordered schedule (igi_fps_balanced) ---------------------------------------------------------
 // The cost of a task grows with the square of its point count (n picks before the early exit x n/32
 // points per lane), and the counts of neighbouring envs differ by up to 6x, so a static assignment
@@ -824,8 +962,31 @@ extern "C" int igi_pcl_sample_gather(const float* pts, const int32_t* count, con
   return IGI_OK;
 }
 
+static int g_fps_cluster = 1;   // igi_fps_set_cluster(0): big tasks go to the one-CTA fps_kernel instead (A/B, tests)
+
 static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const int32_t* sched, const int32_t* order,
                             cudaStream_t st) {
+  int dev0 = 0, sms0 = 148;
+  cudaGetDevice(&dev0);
+  cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+  // Tasks the resident kernels leave (more than FW_COOP_MAXN points) go to thread-block clusters up to FC_MAXN
+  // points; only larger ones (or every task, when m is too large for the resident kernels: min_n == 0) to fps_kernel.
+  const bool all_big = a.count == nullptr && a.n_fixed > FW_COOP_MAXN;   // fixed-size call above the resident sizes
+  // With a schedule the number of big tasks is only known on the device: both kernels are launched and read
+  // sched[4]; without one (igi_fps) every task may be big and the host decides on n_tasks.
+  const bool cluster_ok = g_fps_cluster && (min_n > 0 || all_big) && (sched != nullptr || a.n_tasks <= FC_TASK_LIMIT);
+  if (cluster_ok) {
+    int clusters = sms0 / FC_CL * 3;
+    if (clusters > a.n_tasks) clusters = a.n_tasks;
+    if (clusters < 1) clusters = 1;
+    fps_cluster_kernel<<<clusters * FC_CL, FC_BLOCK, 0, st>>>(a, min_n, sched, order);
+    IGI_CHECK_LAUNCH("fps_cluster_kernel");
+    if (!sched) {
+      if (nmax <= FC_MAXN) return IGI_OK;
+      min_n = FC_MAXN + 1;
+    }
+  }
+  const int cluster_limit = cluster_ok && sched ? FC_TASK_LIMIT : 0;
   // worst-case dynamic smem: nmax points (count is on the device)
   const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
   IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
@@ -840,7 +1001,7 @@ static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   const int grid = a.n_tasks < sms * per_sm ? a.n_tasks : sms * per_sm;
   fps_kernel<<<grid, kFpsBlock, smem, st>>>(a.pts, a.task_stride, a.count, a.any, a.count_stride, a.n_fixed, a.n_tasks,
-                                            a.m, a.out_pts, a.out_stride, a.out_idx, min_n, sched, order);
+                                            a.m, a.out_pts, a.out_stride, a.out_idx, min_n, sched, order, cluster_limit, FC_MAXN);
   IGI_CHECK_LAUNCH("fps_kernel");
   return IGI_OK;
 }
@@ -877,6 +1038,11 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
     IGI_CHECK_LAUNCH("fps_warp_kernel");
   }
   if (need_block) return fps_block_launch(a, nmax, need_warp ? FW_COOP_MAXN + 1 : 0, nullptr, nullptr, st);
+  return IGI_OK;
+}
+
+extern "C" int igi_fps_set_cluster(int enabled) {
+  g_fps_cluster = enabled ? 1 : 0;
   return IGI_OK;
 }
 

@@ -176,7 +176,8 @@ def test_fps_balanced_mixed_sizes(built_lib):
 
 
 @pytest.mark.parametrize("n,m", [(1, 4), (2, 5), (37, 16), (37, 64), (128, 400), (129, 300), (384, 400), (385, 400),
-                                 (400, 400), (513, 64), (1024, 400), (1025, 50), (5184, 400)])
+                                 (400, 400), (513, 64), (1024, 400), (1025, 50), (2048, 33), (3000, 400), (5184, 400),
+                                 (8192, 40), (8193, 24)])
 def test_fps_standalone(built_lib, n, m):
     from isaacgyminsertion_b200.pcl_utils import furthest_point_sample
     rng = np.random.default_rng(n)
@@ -189,6 +190,53 @@ def test_fps_standalone(built_lib, n, m):
     idx = furthest_point_sample(torch.from_numpy(pts).cuda(), m).cpu().numpy()
     for b in range(B):
         assert np.array_equal(idx[b], ofps.furthest_point_sample(pts[b], m)), f"batch {b}"
+
+
+def test_fps_cluster_equals_block_kernel(built_lib):
+    """1025..8192 points: the thread-block-cluster kernel and the one-CTA kernel pick the same indices."""
+    from isaacgyminsertion_b200 import _lib
+    from isaacgyminsertion_b200.pcl_utils import furthest_point_sample
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for n, m in ((1300, 200), (4097, 128), (6500, 64)):
+        pts = (rng.random((7, n, 3)) * 0.5 + 0.1).astype(np.float32)
+        pts[4, 100:200] = pts[4, 0:100]
+        d = torch.from_numpy(pts).cuda()
+        a = furthest_point_sample(d, m).cpu().numpy()
+        try:
+            _lib.check(lib.igi_fps_set_cluster(0), "igi_fps_set_cluster")
+            b = furthest_point_sample(d, m).cpu().numpy()
+        finally:
+            lib.igi_fps_set_cluster(1)
+        assert np.array_equal(a, b), (n, m)
+        assert np.array_equal(a[4], ofps.furthest_point_sample(pts[4], m))
+
+
+def test_fps_balanced_long_list_of_big_tasks(built_lib):
+    """More than 512 tasks above 1024 points: the cluster kernel steps aside (device-side switch on the schedule's
+    big-task count) and the one-CTA kernel serves them; 512 or fewer: the clusters do.  Same indices either way."""
+    import ctypes as c
+    from isaacgyminsertion_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    cap, m = 1100, 12
+    for T in (520, 40):
+        pts = (rng.random((T, cap, 3)) * 0.5 + 0.1).astype(np.float32)
+        counts = np.full(T, 1030, dtype=np.int32)
+        counts[::7] = 300                                   # some resident-size tasks in between
+        d_pts, d_cnt = torch.from_numpy(pts).cuda(), torch.from_numpy(counts).cuda()
+        d_any = torch.ones(T, dtype=torch.int32, device="cuda")
+        idx = torch.full((T, m), -7, dtype=torch.int32, device="cuda")
+        scratch = torch.empty(T + 8, dtype=torch.int32, device="cuda")
+        rc = lib.igi_fps_balanced(_lib.dptr(d_pts), c.c_int64(cap * 3), _lib.dptr(d_cnt), _lib.dptr(d_any), c.c_int64(1),
+                                  c.c_int(T), c.c_int(m), None, c.c_int64(m * 3), _lib.dptr(idx), _lib.dptr(scratch),
+                                  _lib.stream_ptr(d_pts.device))
+        _lib.check(rc, "igi_fps_balanced")
+        assert int(scratch[4]) == int((counts > 1024).sum())
+        got = idx.cpu().numpy()
+        for t in list(range(0, T, 37)) + [T - 1]:
+            assert np.array_equal(got[t], ofps.furthest_point_sample(pts[t, :counts[t]], m)), (T, t)
+        assert (got >= 0).all()
 
 
 def test_non_tma_path_matches(built_lib):
