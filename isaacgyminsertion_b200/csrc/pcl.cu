@@ -39,9 +39,10 @@ struct CompactParams {
 // consecutive pixels (one 128-bit shared load of depth, one of seg), a warp 128:
 //   phase A  lanes unproject / transform / box-test only their pixels of a wanted class (most of the
 //            image is background: two compares per pixel) and leave a 4-bit keep mask per class
-//   scan     block-wide exclusive scan of the per-lane keep counts, one class after the other
-//   phase B  lanes with kept pixels recompute the points (same instruction sequence, same bits) and
-//            store them at their offsets
+//   scan     ONE block-wide exclusive scan per class pair: a thread owns consecutive entries and the two
+//            classes' kept counts travel packed in one 32-bit word (two barriers per pair)
+//   phase B  threads recompute their kept points (same instruction sequence, same bits) and store them
+//            at their offsets
 struct CompactEval {
   const float* A;   // ext, row-vector: w = [px,py,pz,1] @ A
   const float* B;   // inverse(env_to_global): o = w @ B^T
@@ -86,7 +87,6 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   __shared__ uint64_t s_bar;
   __shared__ int s_wsum[NW];
   __shared__ int s_warp_any[NW];
-  __shared__ int s_carry;
   __shared__ float s_m[32];  // ext (16) + e2g_inv (16)
 
   const int env = blockIdx.x;
@@ -186,34 +186,45 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   }
   __syncthreads();
 
-  // ---- per class: block scan over the entries in pixel order (256 consecutive entries per round, so
-  // the scan order is the pixel order), then phase B for that class
-  for (int c = 0; c < NC; ++c) {
-    if (tid == 0) s_carry = 0;
+  // ---- ONE block scan for up to two classes at a time: thread t owns the consecutive entries
+  // [t*ept, (t+1)*ept) - pixel order = thread order - and the kept counts of a class pair travel packed in one
+  // 32-bit word (16 bits each: a class keeps fewer than 65536 points), so the whole compaction costs two
+  // barriers per class pair instead of three per 256 entries per class.  Phase B then walks the thread's
+  // entries in order and stores the kept points at the thread's offsets.
+  const int ept = (nq + kCompactBlock - 1) / kCompactBlock;
+  const int q_lo = min(tid * ept, nq), q_hi = min(q_lo + ept, nq);
+  for (int c0 = 0; c0 < NC; c0 += 2) {
+    uint32_t packed = 0;
+    for (int q = q_lo; q < q_hi; ++q) {
+      const uint32_t k = s_keep[q];
+      packed += (uint32_t)__popc((k >> (4 * c0)) & 15u);
+      if (c0 + 1 < NC) packed += (uint32_t)__popc((k >> (4 * c0 + 4)) & 15u) << 16;
+    }
+    uint32_t incl = packed;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, sft);
+      if (lane >= sft) incl += t;
+    }
+    __syncthreads();   // the previous pair's readers of s_wsum are done
+    if (lane == 31) s_wsum[warp] = (int)incl;
     __syncthreads();
-    float* out = p.out_pts + ((size_t)env * NC + c) * (size_t)npix * 3;
-    const int sid_c = p.seg_ids[c];
-    for (int q0 = 0; q0 < nq; q0 += kCompactBlock) {
-      const int q = q0 + tid;
-      const uint32_t m = q < nq ? (s_keep[q] >> (4 * c)) & 15u : 0u;
-      const int cnt = __popc(m);
-      int incl = cnt;
+    uint32_t woff = 0, total = 0;
 #pragma unroll
-      for (int sft = 1; sft < 32; sft <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, sft);
-        if (lane >= sft) incl += t;
-      }
-      if (lane == 31) s_wsum[warp] = incl;
-      __syncthreads();
-      int woff = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const int t = s_wsum[w];
-        if (w < warp) woff += t;
-        total += t;
-      }
-      int slot = s_carry + woff + incl - cnt;
-      if (m) {
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t t = (uint32_t)s_wsum[w];
+      if (w < warp) woff += t;
+      total += t;
+    }
+    const uint32_t excl = woff + incl - packed;
+    for (int cc = 0; cc < 2 && c0 + cc < NC; ++cc) {
+      const int c = c0 + cc;
+      float* out = p.out_pts + ((size_t)env * NC + c) * (size_t)npix * 3;
+      const int sid_c = p.seg_ids[c];
+      int slot = (int)((excl >> (16 * cc)) & 0xffffu);
+      for (int q = q_lo; q < q_hi; ++q) {
+        const uint32_t m = (s_keep[q] >> (4 * c)) & 15u;
+        if (!m) continue;
         const float4 d4 = reinterpret_cast<const float4*>(s_depth)[q];
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -231,16 +242,13 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
           ++slot;
         }
       }
-      __syncthreads();   // everyone has read s_carry / s_wsum
-      if (tid == 0) s_carry += total;
-      __syncthreads();
-    }
-    if (tid == 0) {
-      int bany = 0;
+      if (tid == 0) {
+        int bany = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) bany |= (s_warp_any[w] >> c) & 1;
-      p.out_count[(size_t)env * NC + c] = s_carry;
-      p.out_any[(size_t)env * NC + c] = bany;
+        for (int w = 0; w < NW; ++w) bany |= (s_warp_any[w] >> c) & 1;
+        p.out_count[(size_t)env * NC + c] = (int)((total >> (16 * cc)) & 0xffffu);
+        p.out_any[(size_t)env * NC + c] = bany;
+      }
     }
   }
 }
