@@ -64,3 +64,21 @@ def test_gather_observations_world2_gloo(total):
 def test_single_process_gather_is_identity():
     x = torch.randn(5, 7)
     assert igdist.gather_observations(x) is x
+
+
+def test_sharded_synthetic_inputs_equal_the_single_gpu_inputs():
+    """bench.make_inputs(E, rank*E, total) over the ranks == make_inputs(total, 0, total): poses, mesh / background
+    ids, depth and segmentation frames are functions of the GLOBAL env id, so the work is the same however the envs
+    are sharded (the NCCL run then gathers rows that equal the single-GPU rows bit-for-bit, tools/check_gather_nccl.py)."""
+    import numpy as np
+    import bench
+    total, world = 6, 2
+    _, P, depth, seg = bench.make_inputs(total, 0, total)
+    E = total // world
+    for r in range(world):
+        _, Pr, dr, sr = bench.make_inputs(E, r * E, total)
+        sl = slice(r * E, (r + 1) * E)
+        for k in ("finger_pos", "finger_quat", "plug_pos", "plug_quat", "mesh_id", "bg_id"):
+            assert np.array_equal(Pr[k], P[k][sl]), k
+        assert np.array_equal(sr, seg[sl])
+        assert np.array_equal(dr, depth[sl], equal_nan=True)
