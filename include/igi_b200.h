@@ -226,6 +226,14 @@ int igi_tactile_set_region_budget(int pixels);
  * writes; the contact kernel writes the others.  Results do not depend on the split. */
 int igi_tactile_set_fill_split(int geom_parts);
 
+/* Experimental (round 2 measurement): parts of the no-contact result (1 colour, 2 gel_depth, 4 obs) that the caller
+ * has already written into the output buffers of the NEXT igi_tactile_render calls (e.g. gel_depth zeroed by the
+ * copy engines one step ahead into a second buffer); neither kernel writes them.  0 = none (default). */
+int igi_tactile_set_prefilled(int parts);
+
+/* cudaMemsetAsync on `stream` (a memory operation the DMA engines can run beside the kernels). */
+int igi_memset_async(void* dst, int value, unsigned long long bytes, void* stream);
+
 /* K3 alone: color (F,H,W,3) u8 -> obs.  Replaces factory_task_insertion.py:546-574. */
 int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,
                     int64_t obs_stride, void* stream);
@@ -317,6 +325,12 @@ int igi_traj_gather(void* buf, const int32_t* ids, const int32_t* n_ids, int max
 
 /* counter[ids[j]] = 0 for j < min(*n_ids, max_ids)   (_reset_buffers, experience.py:420). */
 int igi_traj_reset_counters(long long* counter, const int32_t* ids, const int32_t* n_ids, int max_ids, void* stream);
+
+/* dst[r, :] = src[r, :] for the rows r whose flag[r] != 0 equals want != 0; rows of row_bytes (multiple of 16) bytes.
+ * Used to carry frames an update mask leaves untouched (factory_task_insertion.py:523,578-579) from one output buffer to
+ * the other when outputs are double-buffered over steps. */
+int igi_copy_rows_where(void* dst, const void* src, const uint8_t* flag, int want, long long rows, long long row_bytes,
+                        void* stream);
 
 #ifdef __cplusplus
 }

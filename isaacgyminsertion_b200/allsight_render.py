@@ -240,7 +240,8 @@ class BatchedAllSight:
     """Every allsight sensor of an env slice, rendered together on one CUDA device."""
 
     def __init__(self, num_envs, mesh_ids, bg_ids=None, device="cuda", sensors_per_env=3, meshes=None,
-                 sensor_yml=_assets.SENSOR_YML, assets_path=_assets.ASSETS_NPZ, kmax=2048, seed=None):
+                 sensor_yml=_assets.SENSOR_YML, assets_path=_assets.ASSETS_NPZ, kmax=2048, seed=None,
+                 prefill_gel_depth=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedAllSight needs a CUDA device (no CPU fallback)")
@@ -296,6 +297,16 @@ class BatchedAllSight:
         self.color = torch.empty((self.N, self.S, H, W, 3), dtype=torch.uint8, device=dev)
         self.gel_depth = torch.empty((self.N, self.S, H, W), dtype=torch.float32, device=dev)
         self.obs = torch.zeros((self.N, self.S, OBS_LEN), dtype=torch.float32, device=dev)
+        # Experimental (off): gel_depth double-buffered over steps, the buffer of the
+        # NEXT step zeroed by cudaMemsetAsync on a side stream while this step's kernels run, so that neither
+        # kernel spends issue slots / bulk copies on the 200 KB of zeros per frame.
+        self.prefill_gel_depth = bool(prefill_gel_depth)
+        if self.prefill_gel_depth:
+            self._gel_bufs = [self.gel_depth, torch.empty_like(self.gel_depth)]
+            self._gel_idx = 0
+            self._gel_zero_ev = [None, None]          # event of the memset that zeroed buffer i (None: not zeroed)
+            self._gel_side = torch.cuda.Stream(device=dev)
+            self._gel_start_ev = torch.cuda.Event()
         # scratch
         self._M = torch.empty((self.F, 12), dtype=torch.float32, device=dev)
         self._setups = torch.empty((self.F, self.kmax, 16), dtype=torch.int32, device=dev)
@@ -399,11 +410,45 @@ class BatchedAllSight:
             fr.update = None
         fr.mesh_id, fr.bg_id = self.mesh_id.data_ptr(), self.bg_index.data_ptr()
         fr.stage_mask = int(stage_mask)
+        prefilled = 0
+        if self.prefill_gel_depth and stage_mask == 0:
+            cur_stream = torch.cuda.current_stream(self.device)
+            nxt = 1 - self._gel_idx                    # this step renders into the other buffer ...
+            other = self._gel_idx                      # ... and the one used last step is zeroed for the step after
+            if self._gel_zero_ev[nxt] is not None:
+                cur_stream.wait_event(self._gel_zero_ev[nxt])
+            if update is not None:
+                # envs whose update flag is off keep last step's frames (task :523,578-579): carried across first
+                per_env = self.S * self._gel_bufs[0][0, 0].numel() * 4
+                _lib.check(self.lib.igi_copy_rows_where(
+                    _c.c_void_p(self._gel_bufs[nxt].data_ptr()), _c.c_void_p(self._gel_bufs[other].data_ptr()),
+                    _c.c_void_p(fr.update), _c.c_int(0), _c.c_longlong(self.N), _c.c_longlong(per_env),
+                    _lib.stream_ptr(self.device)), "igi_copy_rows_where")
+            self._gel_start_ev.record(cur_stream)      # everything enqueued so far may still read `other`
+            self._gel_side.wait_event(self._gel_start_ev)
+            ob = self._gel_bufs[other]
+            _lib.check(self.lib.igi_memset_async(_c.c_void_p(ob.data_ptr()), _c.c_int(0),
+                                                 _c.c_ulonglong(ob.numel() * 4), _c.c_void_p(self._gel_side.cuda_stream)),
+                       "igi_memset_async")
+            ev = torch.cuda.Event()
+            ev.record(self._gel_side)
+            self._gel_zero_ev[other] = ev
+            if self._gel_zero_ev[nxt] is not None:     # zeroed during the previous step (waited for above)
+                self._gel_zero_ev[nxt] = None          # consumed: the kernels below write into it
+                prefilled = 2
+            self._gel_idx = nxt
+            self.gel_depth = self._gel_bufs[nxt]
         out = IgiTactileOut()
         out.color, out.gel_depth, out.obs = self.color.data_ptr(), self.gel_depth.data_ptr(), obs.data_ptr()
         out.obs_env_stride, out.obs_sensor_stride = obs.stride(0), obs.stride(1)
-        rc = self.lib.igi_tactile_render(_c.byref(self._m), _c.byref(self._st), _c.byref(fr), _c.byref(self._sc),
-                                         _c.byref(out), _lib.stream_ptr(self.device))
+        if prefilled:
+            _lib.check(self.lib.igi_tactile_set_prefilled(prefilled), "igi_tactile_set_prefilled")
+        try:
+            rc = self.lib.igi_tactile_render(_c.byref(self._m), _c.byref(self._st), _c.byref(fr), _c.byref(self._sc),
+                                             _c.byref(out), _lib.stream_ptr(self.device))
+        finally:
+            if prefilled:
+                self.lib.igi_tactile_set_prefilled(0)
         _lib.check(rc, "igi_tactile_render")
         return obs
 

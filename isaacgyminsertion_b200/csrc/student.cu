@@ -281,6 +281,20 @@ __global__ void __launch_bounds__(256) queue_push_kernel(float* q, const TIn* __
   }
 }
 
+// dst[r, :] = src[r, :] for the rows whose flag equals `want` (rows of row16 uint4 each); rows that do not match cost
+// one flag read.  grid = (chunks, rows).
+__global__ void __launch_bounds__(256) copy_rows_where_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                              const uint8_t* __restrict__ flag, int want, long long rows,
+                                                              long long row16) {
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    if ((flag[r] != 0) != (want != 0)) continue;
+    const uint4* s = src + (size_t)r * row16;
+    uint4* d = dst + (size_t)r * row16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row16; i += (long long)gridDim.x * blockDim.x)
+      __stcs(d + i, __ldcs(s + i));
+  }
+}
+
 int grid_for(long long work_items, int block, int cap = 148 * 16) {
   long long g = (work_items + block - 1) / block;
   if (g < 1) g = 1;
@@ -381,5 +395,21 @@ extern "C" int igi_queue_push(float* queue, const void* x, int x_is_int32, int64
     queue_push_kernel<float><<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
         queue, reinterpret_cast<const float*>(x), x_stride, n_envs, hist_len, row_len / 4);
   IGI_CHECK_LAUNCH("queue_push_kernel");
+  return IGI_OK;
+}
+
+extern "C" int igi_copy_rows_where(void* dst, const void* src, const uint8_t* flag, int want, long long rows,
+                                   long long row_bytes, void* stream) {
+  IGI_REQUIRE(dst && src && flag, "igi_copy_rows_where: null pointer");
+  IGI_REQUIRE(rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0, "igi_copy_rows_where: row_bytes must be a positive multiple of 16");
+  IGI_REQUIRE(((uintptr_t)dst % 16) == 0 && ((uintptr_t)src % 16) == 0, "igi_copy_rows_where: buffers must be 16-byte aligned");
+  if (rows == 0) return IGI_OK;
+  const long long row16 = row_bytes / 16;
+  long long gx = (row16 + 255) / 256;
+  if (gx > 32) gx = 32;
+  const long long gy = rows < 65535 ? rows : 65535;
+  copy_rows_where_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
+      (uint4*)dst, (const uint4*)src, flag, want, rows, row16);
+  IGI_CHECK_LAUNCH("copy_rows_where_kernel");
   return IGI_OK;
 }

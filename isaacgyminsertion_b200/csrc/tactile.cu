@@ -1437,6 +1437,20 @@ extern "C" int igi_tactile_set_fill_split(int geom_parts) {
   return IGI_OK;
 }
 
+static int g_fill_prefilled_parts = 0;  // fill parts the caller wrote itself before the call (neither kernel writes them)
+
+extern "C" int igi_tactile_set_prefilled(int parts) {
+  IGI_REQUIRE(parts >= 0 && parts <= 7, "igi_tactile_set_prefilled: parts mask must be 0..7");
+  g_fill_prefilled_parts = parts;
+  return IGI_OK;
+}
+
+extern "C" int igi_memset_async(void* dst, int value, unsigned long long bytes, void* stream) {
+  IGI_REQUIRE(dst != nullptr, "igi_memset_async: null pointer");
+  IGI_CUDA(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
+  return IGI_OK;
+}
+
 extern "C" int igi_tactile_set_region_budget(int pixels) {
   IGI_REQUIRE(pixels == 0 || pixels >= (2 * HALO + 1) * (2 * HALO + 1), "igi_tactile_set_region_budget: need 0 or >= 49 pixels");
   g_region_budget = pixels;
@@ -1551,7 +1565,8 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   // In the fused modes (no bit 1 / 2) the fill is split between the two kernels: tac_geom writes
   // g_fill_geom_parts, tac_contact the rest (it then visits every live frame, not only those with candidates).
   const bool fused = (stages & 3) == 0;
-  const int parts_geom = fused ? g_fill_geom_parts : 0, parts_contact = fused ? (7 & ~g_fill_geom_parts) : 0;
+  const int parts_geom = fused ? (g_fill_geom_parts & ~g_fill_prefilled_parts) : 0,
+            parts_contact = fused ? (7 & ~g_fill_geom_parts & ~g_fill_prefilled_parts) : 0;
   // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
   if (stages & 9) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
   else IGI_CUDA(cudaMemsetAsync(sc->counters + 1, 0, sizeof(int32_t), s));

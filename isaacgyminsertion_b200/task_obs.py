@@ -53,7 +53,7 @@ class FactoryTaskInsertionTactileObs:
     def __init__(self, num_envs, gym, mesh_ids, bg_ids=None, device="cuda", num_points=400, num_points_socket=400,
                  tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=2048,
                  strict_rng=True, pcl_noise_enabled=False, overlap_streams=True, include_all_pcl=False,
-                 total_points=2048):
+                 total_points=2048, prefill_gel_depth=False):
         self.device = torch.device(device)
         self.num_envs = num_envs
         self.fingertips = ["finger_1_3", "finger_2_3", "finger_3_3"]   # factory_env_insertion.py:748
@@ -94,7 +94,8 @@ class FactoryTaskInsertionTactileObs:
         self.tactile = tactile
         self.pcl_cam = pcl_cam
         if tactile:
-            self.tactile_engine = BatchedAllSight(N, mesh_ids, bg_ids, device=dev, kmax=kmax)
+            self.tactile_engine = BatchedAllSight(N, mesh_ids, bg_ids, device=dev, kmax=kmax,
+                                                  prefill_gel_depth=prefill_gel_depth)
             self.tactile_handles = None    # built lazily by `handles()`
         if pcl_cam:
             self.pcl_generator = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props,

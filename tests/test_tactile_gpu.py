@@ -156,3 +156,23 @@ def test_coloured_lights_use_three_channel_path(built_lib, tmp_path):
         assert np.array_equal(eng.gel_depth[e, n].cpu().numpy(), w["gel_depth"])
         assert np.abs(eng.color[e, n].cpu().numpy().astype(int) - w["color"].astype(int)).max() <= 1
         assert np.abs(eng.obs[e, n].cpu().numpy() - w["obs"]).max() <= 1.0 / 255 + 1e-6
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("IGI_TEST_EXPERIMENTAL"),
+                    reason="experimental gel_depth prefill (DESIGN.md section 8 item 0): not measured yet, set IGI_TEST_EXPERIMENTAL=1")
+def test_prefilled_gel_depth_equals_default_path(oracle_model, built_lib):
+    """gel_depth double-buffered and zeroed one step ahead by cudaMemsetAsync == the default path, over several
+    steps with changing poses and with an update mask that keeps some envs' previous frames."""
+    from isaacgyminsertion_b200.allsight_render import BatchedAllSight
+    n = 9
+    Ps = [synthetic.tactile_poses(n, oracle_model.assets, seed=s) for s in (0, 1, 2, 3)]
+    for P in Ps[1:]:
+        P["mesh_id"], P["bg_id"] = Ps[0]["mesh_id"], Ps[0]["bg_id"]        # static per engine
+    ref = BatchedAllSight(n, Ps[0]["mesh_id"], Ps[0]["bg_id"], device="cuda:0")
+    exp = BatchedAllSight(n, Ps[0]["mesh_id"], Ps[0]["bg_id"], device="cuda:0", prefill_gel_depth=True)
+    masks = [None, None, torch.tensor([1, 0, 1, 1, 0, 1, 1, 1, 0], dtype=torch.bool, device="cuda:0"), None]
+    for P, m in zip(Ps, masks):
+        _render(ref, P, update=m)
+        _render(exp, P, update=m)
+        assert torch.equal(ref.gel_depth, exp.gel_depth)
+        assert torch.equal(ref.color, exp.color) and torch.equal(ref.obs, exp.obs)
