@@ -201,7 +201,11 @@ def run_reference(args):
     if rank != 0:
         return
     build_oracle()
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))     # the cores this process may actually use (cgroup / affinity aware)
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(cores, 1)
     n = max(cores * 2, 8)
     gym, P, depth, seg = make_inputs(n, 0, n)
     jobs = cpu_jobs(gym, P, depth, seg, n)
