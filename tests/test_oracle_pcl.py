@@ -128,3 +128,58 @@ def test_fps_oracle_degenerate():
     assert ofps.furthest_point_sample(z, 3).tolist() == [0, 0, 0]
     out, idx = ofps.fps_batch([np.zeros((0, 3)), pts], 4)
     assert not out[0].any() and idx[1][1] == 3
+
+
+def _fps_literal(pts, m):
+    """Literal emulation of the published pointnet2_ops kernel (furthest_point_sampling_kernel): B threads stride over
+    the points keeping the first maximum (strict >), then the shared-memory tree `__update(t, t + s)` for
+    s = B/2 .. 1, where a tie keeps the lower position.  Slow; small cases only."""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    n = len(pts)
+    B = 1 << min(int(np.floor(np.log2(n))), 9)
+    temp = np.full(n, np.float32(1e10), dtype=np.float32)
+    idx = np.zeros(m, dtype=np.int32)
+    old = 0
+    f = np.float32
+    for j in range(1, m):
+        best = np.full(B, f(-1), dtype=np.float32)
+        besti = np.zeros(B, dtype=np.int64)
+        x1, y1, z1 = pts[old]
+        for tid in range(B):
+            for k in range(tid, n, B):
+                x2, y2, z2 = pts[k]
+                mag = f(f(x2 * x2) + f(y2 * y2)) + f(z2 * z2)
+                if mag <= f(1e-3):
+                    continue
+                dx, dy, dz = f(x2 - x1), f(y2 - y1), f(z2 - z1)
+                d = f(f(f(dx * dx) + f(dy * dy)) + f(dz * dz))
+                d2 = min(d, temp[k])
+                temp[k] = d2
+                if d2 > best[tid]:
+                    best[tid], besti[tid] = d2, k
+        s = B // 2
+        while s >= 1:
+            for t in range(s):
+                if best[t + s] > best[t]:
+                    best[t], besti[t] = best[t + s], besti[t + s]
+            s //= 2
+        old = int(besti[0])
+        idx[j] = old
+    return idx
+
+
+def test_fps_tie_rule_equals_literal_block_reduction():
+    """The vectorised oracle's tie key (bit-reversed k mod B, then k) == the outcome of the literal strided scan +
+    tree reduction, including exact distance ties, identical points and never-candidate points."""
+    rng = np.random.default_rng(4)
+    for n, m in ((1, 3), (2, 4), (5, 8), (37, 20), (70, 40), (130, 24)):
+        pts = (rng.random((n, 3)) * 0.5 + 0.1).astype(np.float32)
+        cases = [pts]
+        if n >= 5:
+            dup = pts.copy(); dup[n // 2:] = dup[: n - n // 2]; cases.append(dup)          # exact ties
+            same = pts.copy(); same[:] = same[0]; cases.append(same)                         # all identical
+            zer = pts.copy(); zer[::3] = 0.0; cases.append(zer)                              # |p|^2 <= 1e-3
+            grid = (np.stack(np.meshgrid(np.arange(4), np.arange(4), np.arange(4)), -1).reshape(-1, 3)[:n] * 0.25 + 0.25)
+            cases.append(grid.astype(np.float32))                                             # lattice: many equal distances
+        for c in cases:
+            assert np.array_equal(ofps.furthest_point_sample(c, m), _fps_literal(c, m)), (n, m)
