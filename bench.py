@@ -43,8 +43,6 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--prefill-gel-depth", action="store_true",
-                    help="experimental: gel_depth double-buffered, zeroed one step ahead by cudaMemsetAsync on a side stream")
     ap.add_argument("--sync-gather", action="store_true", help="do not overlap the all-gather with the next step")
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
     ap.add_argument("--no-overlap", action="store_true", help="point-cloud path on the same stream as the tactile path")
@@ -260,8 +258,7 @@ def main():
     total = E * world
     gym, P, depth_np, seg_np = make_inputs(E, rank * E, total)
     task = FactoryTaskInsertionTactileObs(E, gym, P["mesh_id"], P["bg_id"], device=dev, sampler=args.sampler,
-                                          strict_rng=False, overlap_streams=not args.no_overlap,
-                                          prefill_gel_depth=args.prefill_gel_depth)
+                                          strict_rng=False, overlap_streams=not args.no_overlap)
 
     # pinned host staging (the e2e leg copies from / to these every step)
     def pin(a):

@@ -86,10 +86,14 @@ int igi_pcl_sample_gather(const float* pts, const int32_t* count, const int32_t*
  *   any     (n_tasks) i32 or NULL: tasks with any==0 produce zeros (pcl_utils.py:179-183)
  *   out_pts (n_tasks, m, 3) f32 gathered points or NULL, row stride out_stride floats
  *   out_idx (n_tasks, m) i32 or NULL
+ *   flags   0, or IGI_FPS_NO_CLUSTER: tasks of 1025..8192 points, which normally run on thread-block clusters
+ *           (4 CTAs x 256 threads, candidates exchanged through distributed shared memory), go to the one-CTA
+ *           kernel instead (same results; for A/B timing and tests)
  */
+#define IGI_FPS_NO_CLUSTER 1
 int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
             int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts, int64_t out_stride,
-            int32_t* out_idx, void* stream);
+            int32_t* out_idx, int flags, void* stream);
 
 /* K5B with a size-ordered schedule.  Same results as igi_fps for device-side counts; the tasks
  * are first counting-sorted by point count (descending) and persistent CTAs pull them longest
@@ -102,25 +106,22 @@ int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const i
  */
 int igi_fps_balanced(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
                      int64_t count_stride, int n_tasks, int m, float* out_pts, int64_t out_stride,
-                     int32_t* out_idx, int32_t* scratch, void* stream);
-
-/* Tasks of 1025..8192 points run on thread-block clusters (4 CTAs x 256 threads, candidates exchanged through
- * distributed shared memory); enabled = 0 sends them to the one-CTA kernel instead (same results; for A/B timing). */
-int igi_fps_set_cluster(int enabled);
+                     int32_t* out_idx, int32_t* scratch, int flags, void* stream);
 
 /* --------------------------------------------------------------------------
  * (T) allsight tactile renderer
  * -------------------------------------------------------------------------- */
 
-/* Sensor constants (host memory; copied to __constant__).  Values come from the sensor
- * yaml the reference loads at tacto/renderer.py:86-87 (config_allsight_white.yml) and from
- * tacto_allsight_wrapper/allsight_wrapper.py:100-174 (spot lights), expressed in the
- * CAMERA frame (camera at the origin looking down -z, OpenGL convention). */
+/* Sensor constants (host memory).  They travel with every call and reach the kernels as a kernel parameter, so
+ * the library keeps NO sensor state: engines with different sensor yamls, or on different devices, can share a
+ * process.  Values come from the sensor yaml the reference loads at tacto/renderer.py:86-87
+ * (config_allsight_white.yml) and from tacto_allsight_wrapper/allsight_wrapper.py:100-174 (spot lights),
+ * expressed in the CAMERA frame (camera at the origin looking down -z, OpenGL convention). */
 typedef struct IgiSensorParams {
   int32_t width, height;        /* 224 x 224 (FactoryTaskInsertionTactile.yaml:31-33) */
   float znear;                  /* yml camera.znear */
-  const float* dxp;             /* (width)  ray slope per column: ((px+.5)/W*2-1)*tan(yfov/2)*aspect */
-  const float* dyp;             /* (height) ray slope per row:    (1-(py+.5)/H*2)*tan(yfov/2)        */
+  float dxp_first, dxp_last;    /* first / last entry of the ray-slope table of the columns (IgiTactileStatic.dxp) */
+  float dyp_first, dyp_last;    /* first / last entry of the ray-slope table of the rows    (IgiTactileStatic.dyp) */
   int32_t n_lights;
   const float* light_pos;       /* (L,3) */
   const float* light_dir;       /* (L,3) unit spot direction */
@@ -128,7 +129,7 @@ typedef struct IgiSensorParams {
   const float* light_int;       /* (L)   */
   const float* light_las;       /* (L) 1/max(.001, cos(inner)-cos(outer)) */
   const float* light_lao;       /* (L) -cos(outer)*las */
-  int32_t inverse_square;       /* 1: radiance / d^2 ; 0: none (yaml lights.falloff) */
+  int32_t inverse_square;       /* 1: radiance / d^2 (default, pyrender); 0: none (yaml lights.falloff, DESIGN.md 'light model') */
   float base_color[3], metallic, roughness;
   double cam_R[9], cam_p[3];    /* camera zero pose in the sensor frame (renderer.py:305-311) */
   double max_force, max_deformation; /* yml force.range_force[1], force.max_deformation */
@@ -139,7 +140,6 @@ typedef struct IgiSensorParams {
   int32_t grid_n[3];
   float depth0_max;
   int32_t hiz_levels, hiz_off[10], hiz_w[10]; /* depth0 max-pyramid layout (IgiTactileStatic.hiz) */
-  float area_w_full, area_w_half; /* cv2 INTER_AREA 3.5x taps as float32: 2/7 and 1/7 */
 } IgiSensorParams;
 
 /* Mesh table (device): all plug meshes concatenated, faces grouped into clusters. */
@@ -160,6 +160,8 @@ typedef struct IgiTactileStatic {
   const float* obs_empty;       /* (2048)  observation of a no-contact frame */
   const float* grid;            /* (nz,ny,nx) distance grid */
   const float* hiz;             /* max-pyramid of depth0, level l at hiz + hiz_off[l], row length hiz_w[l] */
+  const float* dxp;             /* (W) ray slope per column: ((px+.5)/W*2-1)*tan(yfov/2)*aspect */
+  const float* dyp;             /* (H) ray slope per row:    (1-(py+.5)/H*2)*tan(yfov/2)        */
 } IgiTactileStatic;
 
 /* Per-step inputs (device): poses exactly as update_tactile gathers them
@@ -178,6 +180,11 @@ typedef struct IgiTactileFrames {
   int32_t stage_mask;           /* 0 = whole pipeline (= 8|4).  bits: 1 geometry alone, 2 standalone fill,
                                    4 contact, 8 geometry with the fill fused in (excludes 1 and 2).  Single
                                    stages exist for profiling: later ones reuse the scratch of an earlier run */
+  int32_t region_budget;        /* 0 = built-in.  Test hook: cap the pixels (interior + blur halo) one shared-memory
+                                   region of the contact kernel may hold, so small inputs exercise the multi-region path */
+  int32_t fill_split;           /* 0 = built-in.  Tuning hook: parts mask + 1 of the no-contact result (1 colour, 2
+                                   gel_depth, 4 obs) the geometry kernel writes; the contact kernel writes the others.
+                                   Results do not depend on the split */
 } IgiTactileFrames;
 
 typedef struct IgiTactileScratch {
@@ -188,7 +195,10 @@ typedef struct IgiTactileScratch {
   int32_t* counts;              /* (F) */
   int32_t* bbox;                /* (F,4) */
   int32_t* worklist;            /* (F) */
-  int32_t* counters;            /* (4): work_n, cursor, overflow (sticky), reserved */
+  int32_t* counters;            /* (4): work_n, cursor, overflow flag (sticky: a frame produced more than kmax candidate
+                                   triangles and the rest was dropped), largest per-frame candidate count seen (sticky).
+                                   The caller reads [2], [3] when it likes (an asynchronous 8-byte copy per step needs
+                                   no host sync) and clears them */
   int32_t kmax;                 /* <= 4096 */
 } IgiTactileScratch;
 
@@ -201,38 +211,20 @@ typedef struct IgiTactileOut {
   int64_t obs_env_stride, obs_sensor_stride;
 } IgiTactileOut;
 
-/* Upload sensor constants.  Replaces Renderer.__init__/_init_camera/_init_light
- * (tacto/renderer.py:65-163,291-325; allsight_wrapper.py:100-174). */
-int igi_tactile_set_sensor(const IgiSensorParams* p);
-
-/* K0: depth0 + bg_sim of the static gel.  Replaces get_background_sim (renderer.py:165-168).
- * gel_tris (n,3,3) f32 sensor frame; scratch_zbuf (H*W) u64. */
-int igi_tactile_gel_precompute(const float* gel_tris, int n_tris, uint64_t* scratch_zbuf, float* depth0,
-                               uint8_t* bg_sim, void* stream);
+/* K0: depth0 + bg_sim of the static gel.  Replaces Renderer.__init__/_init_camera/_init_light
+ * (tacto/renderer.py:65-163,291-325; allsight_wrapper.py:100-174) and get_background_sim (renderer.py:165-168).
+ * dxp (W) / dyp (H) device ray-slope tables; gel_tris (n,3,3) f32 sensor frame; scratch_zbuf (H*W) u64. */
+int igi_tactile_gel_precompute(const IgiSensorParams* sensor, const float* dxp, const float* dyp, const float* gel_tris,
+                               int n_tris, uint64_t* scratch_zbuf, float* depth0, uint8_t* bg_sim, void* stream);
 
 /* K1+K2+K3 for every env x sensor frame.  Replaces the hot loop of _render_tactile
  * (factory_task_insertion.py:515-583): update_pose_given_sim_pose (allsight_render.py:168-172),
  * AllSightRenderer.render (:179-212) -> Renderer.render/adjust_with_force/pyrender draw
  * (tacto/renderer.py:560-648), _calibrate (allsight_wrapper.py:57-98), depth0-depth, remove_bg,
  * mask, flipud, crop, INTER_AREA resize, gray (task :546-574). */
-int igi_tactile_render(const IgiTactileMeshes* meshes, const IgiTactileStatic* st, const IgiTactileFrames* frames,
-                       const IgiTactileScratch* scratch, const IgiTactileOut* out, void* stream);
-
-/* Test hook: cap the pixels (interior + blur halo) one shared-memory region of the contact kernel may
- * hold, so small inputs exercise the multi-region path.  0 restores the built-in budget. */
-int igi_tactile_set_region_budget(int pixels);
-
-/* Tuning hook: which parts of the no-contact result (1 colour, 2 gel_depth, 4 obs) the geometry kernel
- * writes; the contact kernel writes the others.  Results do not depend on the split. */
-int igi_tactile_set_fill_split(int geom_parts);
-
-/* Experimental (round 2 measurement): parts of the no-contact result (1 colour, 2 gel_depth, 4 obs) that the caller
- * has already written into the output buffers of the NEXT igi_tactile_render calls (e.g. gel_depth zeroed by the
- * copy engines one step ahead into a second buffer); neither kernel writes them.  0 = none (default). */
-int igi_tactile_set_prefilled(int parts);
-
-/* cudaMemsetAsync on `stream` (a memory operation the DMA engines can run beside the kernels). */
-int igi_memset_async(void* dst, int value, unsigned long long bytes, void* stream);
+int igi_tactile_render(const IgiSensorParams* sensor, const IgiTactileMeshes* meshes, const IgiTactileStatic* st,
+                       const IgiTactileFrames* frames, const IgiTactileScratch* scratch, const IgiTactileOut* out,
+                       void* stream);
 
 /* K3 alone: color (F,H,W,3) u8 -> obs.  Replaces factory_task_insertion.py:546-574. */
 int igi_tactile_obs(const uint8_t* color, const uint8_t* bg_real, const int32_t* bg_id, int n_frames, float* obs,
@@ -331,6 +323,30 @@ int igi_traj_reset_counters(long long* counter, const int32_t* ids, const int32_
  * the other when outputs are double-buffered over steps. */
 int igi_copy_rows_where(void* dst, const void* src, const uint8_t* flag, int want, long long rows, long long row_bytes,
                         void* stream);
+
+/* ----------------------------------------------------------------------------
+ * (G) gather of the packed observation rows onto the learner rank without SM work.
+ * The reference has no counterpart: its ranks exchange gradients only (algo/ext_adapt/ext_adapt.py:833-851,
+ * isaacgyminsertion/train.py:58-64 one process per GPU); the north star adds "all-gather observations onto
+ * the learner rank".  isaacgyminsertion_b200/dist.py `ObsGather(transport="p2p")` is the host side: every
+ * rank copies its rows straight into the learner's buffer (a cudaMalloc block shared over CUDA IPC) with a
+ * copy-engine peer copy and publishes the step number with a second 4-byte copy; waits are stream memory
+ * operations on the waiter's OWN memory.  No kernel is launched by any of these entry points.
+ * -------------------------------------------------------------------------- */
+
+/* G1  cudaMalloc a zeroed block and export its 64-byte CUDA IPC handle (the one place this library allocates:
+ *     IPC handles exist only for whole allocations).  Release with igi_peer_free. */
+int igi_peer_alloc(unsigned long long bytes, void** ptr_out, unsigned char* handle64_out);
+int igi_peer_free(void* ptr);
+/* G2  map another process's block (cudaIpcMemLazyEnablePeerAccess) / unmap it. */
+int igi_peer_open(const unsigned char* handle64, void** ptr_out);
+int igi_peer_close(void* ptr);
+/* G3  dst <- src (bytes) on `stream`, devices resolved by unified addressing: a copy-engine transfer over NVLink. */
+int igi_peer_copy_async(void* dst, const void* src, unsigned long long bytes, void* stream);
+/* G4  stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32 with CU_STREAM_WAIT_VALUE_GEQ, cyclic
+ *     comparison) on a 4-byte-aligned device address of the calling device. */
+int igi_stream_write_value32(void* stream, void* addr, unsigned int value);
+int igi_stream_wait_value32_geq(void* stream, void* addr, unsigned int value);
 
 #ifdef __cplusplus
 }

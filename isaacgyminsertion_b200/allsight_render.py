@@ -32,7 +32,8 @@ OBS_LEN = OBS_W * OBS_H
 class IgiSensorParams(_c.Structure):
     _fields_ = [
         ("width", _c.c_int32), ("height", _c.c_int32), ("znear", _c.c_float),
-        ("dxp", _c.c_void_p), ("dyp", _c.c_void_p), ("n_lights", _c.c_int32),
+        ("dxp_first", _c.c_float), ("dxp_last", _c.c_float), ("dyp_first", _c.c_float), ("dyp_last", _c.c_float),
+        ("n_lights", _c.c_int32),
         ("light_pos", _c.c_void_p), ("light_dir", _c.c_void_p), ("light_col", _c.c_void_p),
         ("light_int", _c.c_void_p), ("light_las", _c.c_void_p), ("light_lao", _c.c_void_p),
         ("inverse_square", _c.c_int32),
@@ -44,7 +45,6 @@ class IgiSensorParams(_c.Structure):
         ("grid_org", _c.c_float * 3), ("grid_h", _c.c_float), ("grid_slack", _c.c_float),
         ("grid_n", _c.c_int32 * 3), ("depth0_max", _c.c_float),
         ("hiz_levels", _c.c_int32), ("hiz_off", _c.c_int32 * 10), ("hiz_w", _c.c_int32 * 10),
-        ("area_w_full", _c.c_float), ("area_w_half", _c.c_float),
     ]
 
 
@@ -55,7 +55,8 @@ class IgiTactileMeshes(_c.Structure):
 
 class IgiTactileStatic(_c.Structure):
     _fields_ = [("depth0", _c.c_void_p), ("bg_sim", _c.c_void_p), ("bg_real", _c.c_void_p),
-                ("obs_empty", _c.c_void_p), ("grid", _c.c_void_p), ("hiz", _c.c_void_p)]
+                ("obs_empty", _c.c_void_p), ("grid", _c.c_void_p), ("hiz", _c.c_void_p),
+                ("dxp", _c.c_void_p), ("dyp", _c.c_void_p)]
 
 
 class IgiTactileFrames(_c.Structure):
@@ -64,7 +65,7 @@ class IgiTactileFrames(_c.Structure):
                 ("plug_pos", _c.c_void_p), ("plug_quat", _c.c_void_p),
                 ("force", _c.c_void_p), ("force_const", _c.c_float),
                 ("update", _c.c_void_p), ("mesh_id", _c.c_void_p), ("bg_id", _c.c_void_p),
-                ("stage_mask", _c.c_int32)]
+                ("stage_mask", _c.c_int32), ("region_budget", _c.c_int32), ("fill_split", _c.c_int32)]
 
 
 class IgiTactileScratch(_c.Structure):
@@ -97,7 +98,7 @@ class SensorConfig:
     """Constants of the sensor yaml in the camera frame (tacto/renderer.py:291-325,
     tacto_allsight_wrapper/allsight_wrapper.py:100-174)."""
 
-    def __init__(self, yml=_assets.SENSOR_YML):
+    def __init__(self, yml=_assets.SENSOR_YML, falloff=None):
         conf = yaml.safe_load(open(yml))["sensor"]
         cam = conf["camera"][0]
         self.cam_zero = euler2matrix(angles=np.deg2rad(cam["orientation"]), translation=cam["position"])
@@ -126,7 +127,12 @@ class SensorConfig:
         self.light_int = np.ascontiguousarray(lg["intensities"], dtype=np.float32)
         self.light_las = np.full(n, las, dtype=np.float32)
         self.light_lao = np.full(n, -np.cos(outer) * las, dtype=np.float32)
-        self.inverse_square = 1 if lg.get("falloff", "none") == "inverse_square" else 0
+        # pyrender attenuates punctual lights by 1/d^2 (KHR_lights_punctual); `none` is the documented
+        # deviation (DESIGN.md "light model").  `falloff` overrides the yaml key.
+        self.falloff = falloff if falloff is not None else lg.get("falloff", "inverse_square")
+        if self.falloff not in ("inverse_square", "none"):
+            raise ValueError(f"lights.falloff must be inverse_square or none, got {self.falloff!r}")
+        self.inverse_square = 1 if self.falloff == "inverse_square" else 0
         self.max_force = float(conf["force"]["range_force"][1])
         self.max_deformation = float(conf["force"]["max_deformation"])
         cal = conf["bg_calibration"]
@@ -240,8 +246,12 @@ class BatchedAllSight:
     """Every allsight sensor of an env slice, rendered together on one CUDA device."""
 
     def __init__(self, num_envs, mesh_ids, bg_ids=None, device="cuda", sensors_per_env=3, meshes=None,
-                 sensor_yml=_assets.SENSOR_YML, assets_path=_assets.ASSETS_NPZ, kmax=2048, seed=None,
-                 prefill_gel_depth=False):
+                 sensor_yml=_assets.SENSOR_YML, assets_path=_assets.ASSETS_NPZ, kmax=1024, seed=None,
+                 falloff=None, on_overflow="grow"):
+        """kmax: triangle-list capacity per frame (scratch = F * kmax * 112 B).  A frame that produces more
+        candidate triangles sets a device flag; `on_overflow` says what the next `render()` call does when it
+        sees the flag of an earlier step (checked without a host sync, see `poll_overflow`): "grow" (default)
+        re-allocates the scratch from the measured high-water mark and warns, "raise" raises."""
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("BatchedAllSight needs a CUDA device (no CPU fallback)")
@@ -249,7 +259,12 @@ class BatchedAllSight:
         self.N, self.S = int(num_envs), int(sensors_per_env)
         self.F = self.N * self.S
         self.kmax = int(kmax)
-        self.cfg = SensorConfig(sensor_yml)
+        if on_overflow not in ("grow", "raise"):
+            raise ValueError("on_overflow must be 'grow' or 'raise'")
+        self.on_overflow = on_overflow
+        self.region_budget = 0      # test hook (IgiTactileFrames.region_budget)
+        self.fill_split = 0         # tuning hook (IgiTactileFrames.fill_split)
+        self.cfg = SensorConfig(sensor_yml, falloff=falloff)
         packed = _assets.load_packed(assets_path)
         if meshes is None:
             meshes = [(packed[f"peg_{i}_v"], packed[f"peg_{i}_vn"], packed[f"peg_{i}_f"])
@@ -276,13 +291,17 @@ class BatchedAllSight:
         # K0 with a provisional (empty) grid, then the real grid from depth0
         self.depth0 = torch.empty((H, W), dtype=torch.float32, device=dev)
         self.bg_sim = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        self._dxp = torch.from_numpy(self.cfg.dxp).to(dev)
+        self._dyp = torch.from_numpy(self.cfg.dyp).to(dev)
         self._grid = torch.zeros((1, 1, 1), dtype=torch.float32, device=dev)
         self._hiz_layout = ([0], [1])
-        self._upload_sensor(np.zeros(3, np.float32), 1.0, 1.0, (1, 1, 1), 1.0)
+        self._sensor = self._sensor_params(np.zeros(3, np.float32), 1.0, 1.0, (1, 1, 1), 1.0)
         zbuf = torch.empty((H * W,), dtype=torch.int64, device=dev)
-        rc = self.lib.igi_tactile_gel_precompute(_lib.dptr(self._gel), _c.c_int(self._gel.shape[0]), _lib.dptr(zbuf),
-                                                 _lib.dptr(self.depth0), _lib.dptr(self.bg_sim),
-                                                 _lib.stream_ptr(dev))
+        with torch.cuda.device(dev):
+            rc = self.lib.igi_tactile_gel_precompute(_c.byref(self._sensor), _lib.dptr(self._dxp), _lib.dptr(self._dyp),
+                                                     _lib.dptr(self._gel), _c.c_int(self._gel.shape[0]), _lib.dptr(zbuf),
+                                                     _lib.dptr(self.depth0), _lib.dptr(self.bg_sim),
+                                                     _lib.stream_ptr(dev))
         _lib.check(rc, "igi_tactile_gel_precompute")
         d0 = self.depth0.cpu().numpy()
         grid, org, h, slack = gel_interior_grid(d0, self.cfg.dxp, self.cfg.dyp)
@@ -290,31 +309,25 @@ class BatchedAllSight:
         hiz, offs, widths = depth_max_pyramid(d0)
         self._hiz = torch.from_numpy(hiz).to(dev)
         self._hiz_layout = (offs, widths)
-        self._upload_sensor(org, h, slack, grid.shape[::-1], float(d0.max()))
+        self._sensor = self._sensor_params(org, h, slack, grid.shape[::-1], float(d0.max()))
         self.mask = circle_mask((W, H))
 
         # persistent outputs (tactile_imgs layout of factory_task_insertion.py:310-314)
         self.color = torch.empty((self.N, self.S, H, W, 3), dtype=torch.uint8, device=dev)
         self.gel_depth = torch.empty((self.N, self.S, H, W), dtype=torch.float32, device=dev)
         self.obs = torch.zeros((self.N, self.S, OBS_LEN), dtype=torch.float32, device=dev)
-        # Experimental (off): gel_depth double-buffered over steps, the buffer of the
-        # NEXT step zeroed by cudaMemsetAsync on a side stream while this step's kernels run, so that neither
-        # kernel spends issue slots / bulk copies on the 200 KB of zeros per frame.
-        self.prefill_gel_depth = bool(prefill_gel_depth)
-        if self.prefill_gel_depth:
-            self._gel_bufs = [self.gel_depth, torch.empty_like(self.gel_depth)]
-            self._gel_idx = 0
-            self._gel_zero_ev = [None, None]          # event of the memset that zeroed buffer i (None: not zeroed)
-            self._gel_side = torch.cuda.Stream(device=dev)
-            self._gel_start_ev = torch.cuda.Event()
         # scratch
         self._M = torch.empty((self.F, 12), dtype=torch.float32, device=dev)
-        self._setups = torch.empty((self.F, self.kmax, 16), dtype=torch.int32, device=dev)
-        self._normals = torch.empty((self.F, self.kmax, 12), dtype=torch.float32, device=dev)
         self._counts = torch.zeros((self.F,), dtype=torch.int32, device=dev)
         self._bbox = torch.zeros((self.F, 4), dtype=torch.int32, device=dev)
         self._work = torch.zeros((self.F,), dtype=torch.int32, device=dev)
         self._counters = torch.zeros((4,), dtype=torch.int32, device=dev)
+        self._alloc_lists()
+        # overflow telemetry: counters[2:4] copied to pinned memory after every render (no host sync)
+        self._ovf_host = torch.zeros((2,), dtype=torch.int32).pin_memory()
+        self._ovf_event = None
+        self._last_args = None
+        self.high_water = 0
         # obs of a frame without contact (color == bg_real): exact for every background id
         self.obs_empty = torch.empty((OBS_LEN,), dtype=torch.float32, device=dev)
         zero_id = torch.zeros((1,), dtype=torch.int32, device=dev)
@@ -326,11 +339,18 @@ class BatchedAllSight:
         self._stage = None
 
     # ------------------------------------------------------------------------------------
-    def _upload_sensor(self, org, h, slack, n_xyz, d0max):
+    def _alloc_lists(self):
+        dev = self.device
+        self._setups = torch.empty((self.F, self.kmax, 16), dtype=torch.int32, device=dev)
+        self._normals = torch.empty((self.F, self.kmax, 12), dtype=torch.float32, device=dev)
+
+    def _sensor_params(self, org, h, slack, n_xyz, d0max):
+        """IgiSensorParams of this engine (host struct, passed with every call: the library keeps no sensor state)."""
         c = self.cfg
         p = IgiSensorParams()
         p.width, p.height, p.znear = W, H, c.znear
-        p.dxp, p.dyp = c.dxp.ctypes.data, c.dyp.ctypes.data
+        p.dxp_first, p.dxp_last = float(c.dxp[0]), float(c.dxp[-1])
+        p.dyp_first, p.dyp_last = float(c.dyp[0]), float(c.dyp[-1])
         p.n_lights = len(c.light_int)
         p.light_pos, p.light_dir, p.light_col = c.light_pos.ctypes.data, c.light_dir.ctypes.data, c.light_col.ctypes.data
         p.light_int, p.light_las, p.light_lao = c.light_int.ctypes.data, c.light_las.ctypes.data, c.light_lao.ctypes.data
@@ -351,10 +371,7 @@ class BatchedAllSight:
         p.hiz_levels = len(offs)
         p.hiz_off = (_c.c_int32 * 10)(*(list(offs) + [0] * (10 - len(offs))))
         p.hiz_w = (_c.c_int32 * 10)(*(list(widths) + [1] * (10 - len(widths))))
-        p.area_w_full = float(np.float32(1.0 / 3.5))
-        p.area_w_half = float(np.float32(0.5 / 3.5))
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.igi_tactile_set_sensor(_c.byref(p)), "igi_tactile_set_sensor")
+        return p
 
     def _structs(self):
         m = IgiTactileMeshes()
@@ -363,6 +380,7 @@ class BatchedAllSight:
         st = IgiTactileStatic()
         st.depth0, st.bg_sim, st.bg_real = self.depth0.data_ptr(), self.bg_sim.data_ptr(), self.bg_real.data_ptr()
         st.obs_empty, st.grid, st.hiz = self.obs_empty.data_ptr(), self._grid.data_ptr(), self._hiz.data_ptr()
+        st.dxp, st.dyp = self._dxp.data_ptr(), self._dyp.data_ptr()
         sc = IgiTactileScratch()
         sc.M, sc.setups, sc.counts = self._M.data_ptr(), self._setups.data_ptr(), self._counts.data_ptr()
         sc.normals = self._normals.data_ptr()
@@ -373,12 +391,14 @@ class BatchedAllSight:
     # ------------------------------------------------------------------------------------
     @torch.no_grad()
     def render(self, finger_pos, finger_quat, plug_pos, plug_quat, force=None, update=None, obs_out=None,
-               stage_mask=0):
+               stage_mask=0, _poll=True):
         """One batched pass.  finger_pos (N,S,3), finger_quat (N,S,4 xyzw), plug_pos (N,3),
         plug_quat (N,4) f32 CUDA tensors; force: None (=70, factory_task_insertion.py:535),
         scalar, or (N,S) tensor; update: None or (N,) bool/uint8 (task :523).
         Fills self.color / self.gel_depth / obs (default self.obs, shape (N,S,2048)); frames of
         envs whose update flag is off are left untouched."""
+        if _poll and stage_mask == 0:
+            self.poll_overflow()
         obs = self.obs if obs_out is None else obs_out
         if obs.shape != (self.N, self.S, OBS_LEN) or obs.stride(-1) != 1 or obs.dtype != torch.float32 \
                 or not obs.is_cuda or obs.data_ptr() % 16 != 0:
@@ -410,52 +430,61 @@ class BatchedAllSight:
             fr.update = None
         fr.mesh_id, fr.bg_id = self.mesh_id.data_ptr(), self.bg_index.data_ptr()
         fr.stage_mask = int(stage_mask)
-        prefilled = 0
-        if self.prefill_gel_depth and stage_mask == 0:
-            cur_stream = torch.cuda.current_stream(self.device)
-            nxt = 1 - self._gel_idx                    # this step renders into the other buffer ...
-            other = self._gel_idx                      # ... and the one used last step is zeroed for the step after
-            if self._gel_zero_ev[nxt] is not None:
-                cur_stream.wait_event(self._gel_zero_ev[nxt])
-            if update is not None:
-                # envs whose update flag is off keep last step's frames (task :523,578-579): carried across first
-                per_env = self.S * self._gel_bufs[0][0, 0].numel() * 4
-                _lib.check(self.lib.igi_copy_rows_where(
-                    _c.c_void_p(self._gel_bufs[nxt].data_ptr()), _c.c_void_p(self._gel_bufs[other].data_ptr()),
-                    _c.c_void_p(fr.update), _c.c_int(0), _c.c_longlong(self.N), _c.c_longlong(per_env),
-                    _lib.stream_ptr(self.device)), "igi_copy_rows_where")
-            self._gel_start_ev.record(cur_stream)      # everything enqueued so far may still read `other`
-            self._gel_side.wait_event(self._gel_start_ev)
-            ob = self._gel_bufs[other]
-            _lib.check(self.lib.igi_memset_async(_c.c_void_p(ob.data_ptr()), _c.c_int(0),
-                                                 _c.c_ulonglong(ob.numel() * 4), _c.c_void_p(self._gel_side.cuda_stream)),
-                       "igi_memset_async")
-            ev = torch.cuda.Event()
-            ev.record(self._gel_side)
-            self._gel_zero_ev[other] = ev
-            if self._gel_zero_ev[nxt] is not None:     # zeroed during the previous step (waited for above)
-                self._gel_zero_ev[nxt] = None          # consumed: the kernels below write into it
-                prefilled = 2
-            self._gel_idx = nxt
-            self.gel_depth = self._gel_bufs[nxt]
+        fr.region_budget, fr.fill_split = int(self.region_budget), int(self.fill_split)
         out = IgiTactileOut()
         out.color, out.gel_depth, out.obs = self.color.data_ptr(), self.gel_depth.data_ptr(), obs.data_ptr()
         out.obs_env_stride, out.obs_sensor_stride = obs.stride(0), obs.stride(1)
-        if prefilled:
-            _lib.check(self.lib.igi_tactile_set_prefilled(prefilled), "igi_tactile_set_prefilled")
-        try:
-            rc = self.lib.igi_tactile_render(_c.byref(self._m), _c.byref(self._st), _c.byref(fr), _c.byref(self._sc),
-                                             _c.byref(out), _lib.stream_ptr(self.device))
-        finally:
-            if prefilled:
-                self.lib.igi_tactile_set_prefilled(0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.igi_tactile_render(_c.byref(self._sensor), _c.byref(self._m), _c.byref(self._st), _c.byref(fr),
+                                             _c.byref(self._sc), _c.byref(out), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_tactile_render")
+        if stage_mask == 0 and _poll:
+            # overflow flag + high-water mark of this step travel to pinned memory behind the kernels (8 bytes,
+            # no host sync); the next render() looks at them
+            self._ovf_host.copy_(self._counters[2:4], non_blocking=True)
+            self._ovf_event = torch.cuda.Event()
+            self._ovf_event.record(torch.cuda.current_stream(self.device))
+            self._last_args = (finger_pos, finger_quat, plug_pos, plug_quat, force, update, obs_out)
         return obs
 
+    # ------------------------------------------------------------------------------------
+    def poll_overflow(self, wait=False):
+        """Look at the overflow flag of the steps rendered so far WITHOUT a host sync (the flag of a step
+        is visible once its 8-byte copy has landed; `wait=True` blocks for the last step).  On overflow:
+        on_overflow == "raise": RuntimeError; "grow": the lists are re-allocated at 1.5 x the measured
+        high-water mark (the retry path) and the last step is rendered again into the same outputs, so at
+        most the steps consumed between the overflow and this call saw clipped frames (a warning says so).
+        Returns True when an overflow was handled."""
+        ev = self._ovf_event
+        if ev is None or not (wait or ev.query()):
+            return False
+        if wait:
+            ev.synchronize()
+        self._ovf_event = None
+        flag, mark = int(self._ovf_host[0]), int(self._ovf_host[1])
+        self.high_water = max(self.high_water, mark)
+        if not flag:
+            return False
+        self._counters[2:4].zero_()
+        if self.on_overflow == "raise" or mark > 4096:
+            raise RuntimeError(f"tactile triangle list overflow: a frame produced {mark} candidate triangles, "
+                               f"kmax is {self.kmax} (limit 4096)")
+        import warnings
+        new = min(max(int(mark * 1.5), self.kmax + 1), 4096)
+        warnings.warn(f"tactile triangle lists overflowed ({mark} > kmax {self.kmax}): scratch grown to {new} and the "
+                      "last step rendered again; earlier steps since the overflow saw clipped frames")
+        self.kmax = new
+        self._alloc_lists()
+        self._structs()
+        if self._last_args is not None:
+            fp, fq, pp, pq, force, update, obs_out = self._last_args
+            self.render(fp, fq, pp, pq, force=force, update=update, obs_out=obs_out, _poll=False)
+        return True
+
     def check_overflow(self):
-        """Raises if a frame produced more candidate triangles than `kmax` (host sync)."""
-        if int(self._counters[2].item()) != 0:
-            raise RuntimeError(f"tactile triangle list overflow: raise kmax (now {self.kmax})")
+        """Host-synchronous check of the last step (tests, debugging): handles an overflow like `poll_overflow`
+        and raises if `on_overflow == "raise"`."""
+        return self.poll_overflow(wait=True)
 
     def contact_counts(self):
         """(N,S) surviving-triangle count per frame of the last render (-1 = not updated)."""

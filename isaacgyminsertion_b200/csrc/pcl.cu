@@ -941,10 +941,14 @@ extern "C" int igi_pcl_compact(const float* depth, const int32_t* seg, const int
   const size_t smem = 2 * ((npix * 4 + 15) & ~(size_t)15) + ((npix + 3) / 4) * 2 + 16;
   IGI_REQUIRE(smem <= 200 * 1024 && npix < 65536, "igi_pcl_compact: image too large for one CTA (%d x %d)", H, W);
   p.use_bulk = ((npix * 4) % 16 == 0) && ((uintptr_t)depth % 16 == 0) && (!seg || (uintptr_t)seg % 16 == 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    IGI_CUDA(cudaFuncSetAttribute(pcl_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  {   // the opt-in shared-memory size is a per-DEVICE function attribute
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    IGI_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      IGI_CUDA(cudaFuncSetAttribute(pcl_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   pcl_compact_kernel<<<n_envs, kCompactBlock, smem, (cudaStream_t)stream>>>(p);
   IGI_CHECK_LAUNCH("pcl_compact_kernel");
@@ -970,10 +974,9 @@ extern "C" int igi_pcl_sample_gather(const float* pts, const int32_t* count, con
   return IGI_OK;
 }
 
-static int g_fps_cluster = 1;   // igi_fps_set_cluster(0): big tasks go to the one-CTA fps_kernel instead (A/B, tests)
-
+// use_cluster = 0 (flag IGI_FPS_NO_CLUSTER of the call): big tasks go to the one-CTA fps_kernel instead (A/B, tests)
 static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const int32_t* sched, const int32_t* order,
-                            cudaStream_t st) {
+                            cudaStream_t st, int use_cluster) {
   int dev0 = 0, sms0 = 148;
   cudaGetDevice(&dev0);
   cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
@@ -982,7 +985,7 @@ static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const
   const bool all_big = a.count == nullptr && a.n_fixed > FW_COOP_MAXN;   // fixed-size call above the resident sizes
   // With a schedule the number of big tasks is only known on the device: both kernels are launched and read
   // sched[4]; without one (igi_fps) every task may be big and the host decides on n_tasks.
-  const bool cluster_ok = g_fps_cluster && (min_n > 0 || all_big) && (sched != nullptr || a.n_tasks <= FC_TASK_LIMIT);
+  const bool cluster_ok = use_cluster && (min_n > 0 || all_big) && (sched != nullptr || a.n_tasks <= FC_TASK_LIMIT);
   if (cluster_ok) {
     int clusters = sms0 / FC_CL * 3;
     if (clusters > a.n_tasks) clusters = a.n_tasks;
@@ -998,14 +1001,14 @@ static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const
   // worst-case dynamic smem: nmax points (count is on the device)
   const size_t smem = (size_t)((nmax + 3) & ~3) * 16;
   IGI_REQUIRE(smem <= 220 * 1024, "igi_fps: %lld points per task exceed shared memory", (long long)nmax);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
   int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
+  IGI_CUDA(cudaGetDevice(&dev));
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static size_t attr_smem[64] = {0};   // per device
+  if (dev < 0 || dev >= 64 || smem > attr_smem[dev]) {
+    IGI_CUDA(cudaFuncSetAttribute(fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
+  }
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   const int grid = a.n_tasks < sms * per_sm ? a.n_tasks : sms * per_sm;
   fps_kernel<<<grid, kFpsBlock, smem, st>>>(a.pts, a.task_stride, a.count, a.any, a.count_stride, a.n_fixed, a.n_tasks,
@@ -1015,19 +1018,22 @@ static int fps_block_launch(const FpsTaskArgs& a, int64_t nmax, int min_n, const
 }
 
 static int fps_warp_attr() {
-  static bool done = false;
-  if (!done) {
+  static bool done[64] = {false};   // per device
+  int dev = 0;
+  IGI_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
     IGI_CUDA(cudaFuncSetAttribute(fps_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
     IGI_CUDA(cudaFuncSetAttribute(fps_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
-    done = true;
+    if (dev >= 0 && dev < 64) done[dev] = true;
   }
   return IGI_OK;
 }
 
 extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
                        int64_t count_stride, int n_fixed, int n_tasks, int m, float* out_pts,
-                       int64_t out_stride, int32_t* out_idx, void* stream) {
+                       int64_t out_stride, int32_t* out_idx, int flags, void* stream) {
   IGI_REQUIRE(pts && (out_pts || out_idx), "igi_fps: null pointer");
+  IGI_REQUIRE((flags & ~IGI_FPS_NO_CLUSTER) == 0, "igi_fps: unknown flag bits");
   IGI_REQUIRE(n_tasks >= 0 && m > 0, "igi_fps: bad dims");
   IGI_REQUIRE(count || n_fixed > 0, "igi_fps: need count or n_fixed");
   IGI_REQUIRE(!out_pts || out_stride >= (int64_t)m * 3, "igi_fps: out_stride < 3*m");
@@ -1045,19 +1051,15 @@ extern "C" int igi_fps(const float* pts, int64_t task_stride, const int32_t* cou
     fps_warp_kernel<<<(n_tasks + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, warp_smem, st>>>(a);
     IGI_CHECK_LAUNCH("fps_warp_kernel");
   }
-  if (need_block) return fps_block_launch(a, nmax, need_warp ? FW_COOP_MAXN + 1 : 0, nullptr, nullptr, st);
-  return IGI_OK;
-}
-
-extern "C" int igi_fps_set_cluster(int enabled) {
-  g_fps_cluster = enabled ? 1 : 0;
+  if (need_block) return fps_block_launch(a, nmax, need_warp ? FW_COOP_MAXN + 1 : 0, nullptr, nullptr, st, !(flags & IGI_FPS_NO_CLUSTER));
   return IGI_OK;
 }
 
 extern "C" int igi_fps_balanced(const float* pts, int64_t task_stride, const int32_t* count, const int32_t* any,
                                 int64_t count_stride, int n_tasks, int m, float* out_pts, int64_t out_stride,
-                                int32_t* out_idx, int32_t* scratch, void* stream) {
+                                int32_t* out_idx, int32_t* scratch, int flags, void* stream) {
   IGI_REQUIRE(pts && count && scratch && (out_pts || out_idx), "igi_fps_balanced: null pointer");
+  IGI_REQUIRE((flags & ~IGI_FPS_NO_CLUSTER) == 0, "igi_fps_balanced: unknown flag bits");
   IGI_REQUIRE(n_tasks >= 0 && m > 0, "igi_fps_balanced: bad dims");
   IGI_REQUIRE(!out_pts || out_stride >= (int64_t)m * 3, "igi_fps_balanced: out_stride < 3*m");
   if (n_tasks == 0) return IGI_OK;
@@ -1066,7 +1068,7 @@ extern "C" int igi_fps_balanced(const float* pts, int64_t task_stride, const int
   IGI_REQUIRE(nmax <= 0xffff, "igi_fps_balanced: at most 65535 points per task");
   const size_t warp_smem = sizeof(float) * 3 * FW_PLANE + (size_t)FW_WARPS * m * 2;
   if (warp_smem > 28 * 1024)   // m too large for the resident kernel: the static path handles it
-    return igi_fps(pts, task_stride, count, any, count_stride, 0, n_tasks, m, out_pts, out_stride, out_idx, stream);
+    return igi_fps(pts, task_stride, count, any, count_stride, 0, n_tasks, m, out_pts, out_stride, out_idx, flags, stream);
   FpsTaskArgs a{pts, task_stride, count, any, count_stride, 0, n_tasks, m, out_pts, out_stride, out_idx};
   int32_t* sched = scratch;
   int32_t* order = scratch + 8;
@@ -1079,6 +1081,6 @@ extern "C" int igi_fps_balanced(const float* pts, int64_t task_stride, const int
   const int want = (n_tasks + FW_WARPS - 1) / FW_WARPS;
   fps_sorted_kernel<<<want < sms * 8 ? want : sms * 8, FW_WARPS * 32, warp_smem, st>>>(a, sched, order);
   IGI_CHECK_LAUNCH("fps_sorted_kernel");
-  if (nmax > FW_COOP_MAXN) return fps_block_launch(a, nmax, FW_COOP_MAXN + 1, sched, order, st);
+  if (nmax > FW_COOP_MAXN) return fps_block_launch(a, nmax, FW_COOP_MAXN + 1, sched, order, st, !(flags & IGI_FPS_NO_CLUSTER));
   return IGI_OK;
 }

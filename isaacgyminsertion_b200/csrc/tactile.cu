@@ -43,11 +43,14 @@ struct TacConst {
   int grid_n[3];
   float depth0_max;
   int hiz_levels, hiz_off[10], hiz_w[10];  // max-pyramid of depth0 (level 0 = full resolution)
-  float area_w[5];  // INTER_AREA 3.5x taps (f32 as cv2 stores them): even dst: w0 w0 w0 w1, odd: w1 w0 w0 w0
+  float sx0, sx1, sy0, sy1;  // dxp[0], dxp[W-1], dyp[0], dyp[H-1]: ends of the ray-slope tables
 };
-__constant__ TacConst kc;
-__constant__ float k_dxp[TW];
-__constant__ float k_dyp[TH];
+// The sensor constants travel with every launch as a __grid_constant__ kernel parameter (constant bank, same
+// access cost as a __constant__ symbol), so two engines with different sensor yamls can share a process and
+// a device and the library keeps no sensor state.  The two 224-entry ray-slope tables are device arrays owned
+// by the caller (IgiTactileStatic.dxp / dyp); the kernels stage them in shared memory.
+// cv2 INTER_AREA 3.5x taps as cv2 stores them (float32 of 1/3.5 and 0.5/3.5): even dst: w0 w0 w0 w1, odd: w1 w0 w0 w0
+constexpr float AREA_W0 = (float)(1.0 / 3.5), AREA_W1 = (float)(0.5 / 3.5);
 
 // ---- spec arithmetic ---------------------------------------------------------------
 struct V3 { float x, y, z; };
@@ -102,7 +105,7 @@ __device__ __forceinline__ bool make_setup(V3 A, V3 B, V3 C, Setup& s) {
 }
 
 // Conservative pixel bbox of the part of the triangle at depth >= znear. Returns false if empty.
-__device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
+__device__ bool tri_bbox(const TacConst& kc, V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
   const float zn = kc.znear;
   float zA = -A.z, zB = -B.z, zC = -C.z;
   if (fmaxf(zA, fmaxf(zB, zC)) < zn) return false;
@@ -122,7 +125,7 @@ __device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
       mnx = fminf(mnx, sx); mxx = fmaxf(mxx, sx); mny = fminf(mny, sy); mxy = fmaxf(mxy, sy);
     }
   }
-  const float sx0 = k_dxp[0], sx1 = k_dxp[TW - 1], sy0 = k_dyp[0], sy1 = k_dyp[TH - 1];
+  const float sx0 = kc.sx0, sx1 = kc.sx1, sy0 = kc.sy0, sy1 = kc.sy1;
   const float kx = (float)(TW - 1) / (sx1 - sx0), ky = (float)(TH - 1) / (sy1 - sy0);
   float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
   float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
@@ -135,15 +138,15 @@ __device__ bool tri_bbox(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
 }
 
 // Same box with reciprocal multiplies (geometry kernel: the +-1 pixel dilation absorbs the ulps).
-__device__ __forceinline__ bool tri_bbox_fast(V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
+__device__ __forceinline__ bool tri_bbox_fast(const TacConst& kc, V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
   const float zn = kc.znear;
   const float zA = -A.z, zB = -B.z, zC = -C.z;
-  if (fminf(zA, fminf(zB, zC)) < zn) return tri_bbox(A, B, C, x0, y0, x1, y1);  // near-plane cases: general path
+  if (fminf(zA, fminf(zB, zC)) < zn) return tri_bbox(kc, A, B, C, x0, y0, x1, y1);  // near-plane cases: general path
   const float ra = __fdividef(1.0f, zA), rb = __fdividef(1.0f, zB), rc = __fdividef(1.0f, zC);
   const float ax = A.x * ra, ay = A.y * ra, bx = B.x * rb, by = B.y * rb, cx = C.x * rc, cy = C.y * rc;
   const float mnx = fminf(ax, fminf(bx, cx)), mxx = fmaxf(ax, fmaxf(bx, cx));
   const float mny = fminf(ay, fminf(by, cy)), mxy = fmaxf(ay, fmaxf(by, cy));
-  const float sx0 = k_dxp[0], sx1 = k_dxp[TW - 1], sy0 = k_dyp[0], sy1 = k_dyp[TH - 1];
+  const float sx0 = kc.sx0, sx1 = kc.sx1, sy0 = kc.sy0, sy1 = kc.sy1;
   const float kx = __fdividef((float)(TW - 1), sx1 - sx0), ky = __fdividef((float)(TH - 1), sy1 - sy0);
   const float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
   const float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
@@ -156,7 +159,7 @@ __device__ __forceinline__ bool tri_bbox_fast(V3 A, V3 B, V3 C, int& x0, int& y0
 }
 
 // coverage + depth of one pixel; returns t (depth) or -1 when not covered / clipped
-__device__ __forceinline__ float cover(const Setup& s, float dx, float dy, float& e1, float& e2, float& esum) {
+__device__ __forceinline__ float cover(float znear, const Setup& s, float dx, float dy, float& e1, float& e2, float& esum) {
   const float e0 = edge_fn(dx, dy, s.n0);
   if (!edge_in(e0, s.n0)) return -1.0f;
   e1 = edge_fn(dx, dy, s.n1);
@@ -165,7 +168,7 @@ __device__ __forceinline__ float cover(const Setup& s, float dx, float dy, float
   if (!edge_in(e2, s.n2)) return -1.0f;
   const float den = edge_fn(dx, dy, s.N);
   const float t = __fdiv_rn(s.det, den);
-  if (!(t >= kc.znear)) return -1.0f;
+  if (!(t >= znear)) return -1.0f;
   esum = add(add(e0, e1), e2);
   return t;
 }
@@ -214,7 +217,7 @@ __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ft
 // NL = number of lights when known at compile time (the loop unrolls and the light constants become
 // immediate constant-bank operands), 0 = kc.n_lights.
 template <int NCH, int NL>
-__device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
+__device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t* rgb) {
   const float A2_PI = kc.sh_a2 * 0.31830988618379067f;
   const float ipl = fast_rsqrt(p.x * p.x + p.y * p.y + p.z * p.z);
   const V3 v{-p.x * ipl, -p.y * ipl, -p.z * ipl};
@@ -262,12 +265,13 @@ __device__ __forceinline__ void shade_t(V3 p, V3 n, uint8_t* rgb) {
   }
   if (NCH == 1) rgb[1] = rgb[2] = rgb[0];
 }
-__device__ __forceinline__ void shade(V3 p, V3 n, uint8_t* rgb) {
-  if (kc.gray) shade_t<1, 0>(p, n, rgb); else shade_t<3, 0>(p, n, rgb);
+__device__ __forceinline__ void shade(const TacConst& kc, V3 p, V3 n, uint8_t* rgb) {
+  if (kc.gray) shade_t<1, 0>(kc, p, n, rgb); else shade_t<3, 0>(kc, p, n, rgb);
 }
 
 // ---- K0: static gel -------------------------------------------------------------------
-__global__ void tac_gel_raster(const float* __restrict__ gel_tris, int G, unsigned long long* __restrict__ zbuf) {
+__global__ void tac_gel_raster(const __grid_constant__ TacConst kc, const float* __restrict__ dxp, const float* __restrict__ dyp,
+                               const float* __restrict__ gel_tris, int G, unsigned long long* __restrict__ zbuf) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const float* t = gel_tris + (size_t)g * 9;
@@ -275,18 +279,19 @@ __global__ void tac_gel_raster(const float* __restrict__ gel_tris, int G, unsign
   Setup s;
   if (!make_setup(A, B, C, s)) return;
   int x0, y0, x1, y1;
-  if (!tri_bbox(A, B, C, x0, y0, x1, y1)) return;
+  if (!tri_bbox(kc, A, B, C, x0, y0, x1, y1)) return;
   for (int py = y0; py <= y1; ++py)
     for (int px = x0; px <= x1; ++px) {
       float e1, e2, es;
-      const float tt = cover(s, k_dxp[px], k_dyp[py], e1, e2, es);
+      const float tt = cover(kc.znear, s, __ldg(dxp + px), __ldg(dyp + py), e1, e2, es);
       if (tt < 0.0f) continue;
       const unsigned long long key = ((unsigned long long)__float_as_uint(tt) << 32) | (uint32_t)g;
       atomicMin(zbuf + (size_t)py * TW + px, key);
     }
 }
 
-__global__ void tac_gel_shade(const float* __restrict__ gel_tris, const unsigned long long* __restrict__ zbuf,
+__global__ void tac_gel_shade(const __grid_constant__ TacConst kc, const float* __restrict__ dxp, const float* __restrict__ dyp,
+                              const float* __restrict__ gel_tris, const unsigned long long* __restrict__ zbuf,
                               float* __restrict__ depth0, uint8_t* __restrict__ bg_sim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= TW * TH) return;
@@ -304,8 +309,8 @@ __global__ void tac_gel_shade(const float* __restrict__ gel_tris, const unsigned
   V3 E1{sub(B.x, A.x), sub(B.y, A.y), sub(B.z, A.z)}, E2{sub(C.x, A.x), sub(C.y, A.y), sub(C.z, A.z)};
   V3 n = normalize(cross3s(E1, E2));
   const int px = i % TW, py = i / TW;
-  V3 p{mul(k_dxp[px], t), mul(k_dyp[py], t), -t};
-  shade(p, n, bg_sim + 3 * i);
+  V3 p{mul(__ldg(dxp + px), t), mul(__ldg(dyp + py), t), -t};
+  shade(kc, p, n, bg_sim + 3 * i);
 }
 
 // ---- K2f: fill -----------------------------------------------------------------------------
@@ -377,6 +382,8 @@ struct GeomArgs {
   const float* grid;         // distance grid
   const float* hiz;          // depth0 max-pyramid
   const float* depth0;       // (TH,TW)
+  const float* dxp;          // (TW) ray slopes per column
+  const float* dyp;          // (TH) ray slopes per row
   float* M_out;              // (F,12)
   Setup* setups;             // (F, kmax)
   const float* vnorm;        // (nv,3) vertex normals, object frame
@@ -385,7 +392,7 @@ struct GeomArgs {
   int32_t* bbox;             // (F,4) dirty window x0,y0,x1,y1
   int32_t* worklist;         // (F)
   int32_t* work_n;           // (1)
-  int32_t* overflow;         // (1)
+  int32_t* overflow;         // (2) sticky overflow flag, largest per-frame triangle count seen
   int sensors_per_env, kmax;
   float force_const;
   int fused_fill;            // 1: this kernel also writes (fill.parts of) the frame's no-contact result
@@ -393,7 +400,7 @@ struct GeomArgs {
   FillArgs fill;
 };
 
-__device__ __forceinline__ float grid_lower_bound(const float* __restrict__ grid, float x, float y, float z) {
+__device__ __forceinline__ float grid_lower_bound(const TacConst& kc, const float* __restrict__ grid, float x, float y, float z) {
   // lower bound of the distance from (x,y,z) (camera frame, depth = -z) to the gel interior
   const float gx = x, gy = y, gz = -z;
   const float lo0 = kc.grid_org[0], lo1 = kc.grid_org[1], lo2 = kc.grid_org[2];
@@ -440,7 +447,7 @@ constexpr int GEOM_WARPS = GEOM_BLOCK / 32;
 #ifndef GEOM_MIN_CTAS
 #define GEOM_MIN_CTAS 9   // 56 registers: 9 CTAs per SM (no bound: 88 regs, 5 CTAs, 0.82 ms; 8: 0.68 ms; 9: 0.65 ms)
 #endif
-__global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a) {
+__global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(const __grid_constant__ TacConst kc, GeomArgs a) {
   __shared__ float sM[12];
   __shared__ int s_cl[GEOM_MAX_CL];
   __shared__ __align__(16) Setup s_q[GEOM_ROUND];   // survivors of the cheap culls of this round
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a
     if (tid == 0) a.counts[f] = -1;  // frame not rendered this step
     return;
   }
-  for (int i = tid; i < TW; i += GEOM_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
+  for (int i = tid; i < TW; i += GEOM_BLOCK) { s_dxp[i] = __ldg(a.dxp + i); s_dyp[i] = __ldg(a.dyp + i); }
   // Fused fill: warps 1.. stream the frame's no-contact result out while lane 0 of warp 0 runs the serial
   // f64 pose chain; the stores drain in the background of the culling work below.  tac_contact, the next
   // kernel on the stream, rewrites the dirty window.
@@ -518,7 +525,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a
   for (int c = tid; c < mi.n_cl; c += GEOM_BLOCK) {
     const Cluster cl = a.clusters[mi.cl_off + c];
     V3 cc = xform(sM, V3{cl.cx, cl.cy, cl.cz});
-    if (grid_lower_bound(a.grid, cc.x, cc.y, cc.z) <= cl.r) {
+    if (grid_lower_bound(kc, a.grid, cc.x, cc.y, cc.z) <= cl.r) {
       const int slot = atomicAdd(&s_ncl, 1);
       if (slot < GEOM_MAX_CL) s_cl[slot] = mi.cl_off + c;
     }
@@ -573,9 +580,9 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a
                 gz = (A.z + B.z + C.z) * (1.0f / 3.0f);
     auto d2 = [&](V3 P) { return (P.x - gx) * (P.x - gx) + (P.y - gy) * (P.y - gy) + (P.z - gz) * (P.z - gz); };
     const float rr = sqrtf(fmaxf(d2(A), fmaxf(d2(B), d2(C)))) * 1.0001f + 1e-7f;
-    if (grid_lower_bound(a.grid, gx, gy, gz) > rr) return false;
+    if (grid_lower_bound(kc, a.grid, gx, gy, gz) > rr) return false;
     CT_COUNT(20, 1);
-    if (!tri_bbox_fast(A, B, C, x0, y0, x1, y1)) return false;
+    if (!tri_bbox_fast(kc, A, B, C, x0, y0, x1, y1)) return false;
     CT_COUNT(21, 1);
     // hierarchical-Z: nearest possible fragment vs the farthest gel depth under the box
     int L = 0;
@@ -685,6 +692,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(GeomArgs a
     const int n = s_count;
     a.counts[f] = min(n, a.kmax);
     if (n > a.kmax || s_ncl > GEOM_MAX_CL) atomicExch(a.overflow, 1);
+    if (n > 0) atomicMax(a.overflow + 1, n);   // high-water mark of the triangle lists: the host sizes `kmax` from it
     if (n > 0) {
       a.bbox[4 * f + 0] = s_bb[0]; a.bbox[4 * f + 1] = s_bb[1];
       a.bbox[4 * f + 2] = s_bb[2]; a.bbox[4 * f + 3] = s_bb[3];
@@ -708,6 +716,8 @@ struct ContactArgs {
   const int32_t* faces;
   const float* depth0;       // (TH,TW)
   const float* hiz;          // depth0 max-pyramid
+  const float* dxp;          // (TW)
+  const float* dyp;          // (TH)
   const uint8_t* bg_sim;     // (TH,TW,3)
   const uint8_t* bg_real;
   const int32_t* bg_id;
@@ -806,13 +816,13 @@ __device__ __forceinline__ void row_span(const Setup& s, float dy, float sx0, fl
 // One fragment: exact coverage + depth, GL_LESS against what the shared z-buffer holds (it starts
 // as the gel depth, so a peg fragment only lands where it is in front of the gel).
 // key = depth bits << 32 | (orig face << 12 | slot) + 1; the gel's key has a zero low word.
-__device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, float dy, unsigned long long* zp, int* s_hits,
+__device__ __forceinline__ void raster_frag(float znear, const Setup& s, int k, float dx, float dy, unsigned long long* zp, int* s_hits,
                                             const float* __restrict__ d0p) {
 #if CT_LAZY_Z
   const float d0 = __ldg(d0p);   // issued first: its latency hides behind the edge functions and the division
 #endif
   float e1, e2, es;
-  const float t = cover(s, dx, dy, e1, e2, es);
+  const float t = cover(znear, s, dx, dy, e1, e2, es);
   if (t < 0.0f) return;
 #if CT_LAZY_Z
   if (d0 != 0.0f && !(t < d0)) return;   // GL_LESS against the gel, which was drawn first (ties keep the gel)
@@ -826,13 +836,13 @@ __device__ __forceinline__ void raster_frag(const Setup& s, int k, float dx, flo
 }
 
 // Fragment of an exact span: inside by construction, only depth (N, det) and the z test.
-__device__ __forceinline__ void raster_frag_depth(V3 N, float det, uint32_t orig, int k, float dx, float dy,
+__device__ __forceinline__ void raster_frag_depth(float znear, V3 N, float det, uint32_t orig, int k, float dx, float dy,
                                                   unsigned long long* zp, int* s_hits, const float* __restrict__ d0p) {
 #if CT_LAZY_Z
   const float d0 = __ldg(d0p);
 #endif
   const float t = __fdiv_rn(det, edge_fn(dx, dy, N));
-  if (!(t >= kc.znear)) return;
+  if (!(t >= znear)) return;
 #if CT_LAZY_Z
   if (d0 != 0.0f && !(t < d0)) return;
 #endif
@@ -845,7 +855,7 @@ __device__ __forceinline__ void raster_frag_depth(V3 N, float det, uint32_t orig
 }
 
 template <int NCH>
-__global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(ContactArgs a) {
+__global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(const __grid_constant__ TacConst kc, ContactArgs a) {
 #ifdef CT_PROFILE
   long long t_prof = clock64();
 #endif
@@ -870,13 +880,13 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   __shared__ __align__(16) float s_zero[CT_ZERO_BYTES / 4];  // source of the asynchronous gel_depth = 0 fill
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CT_BLOCK / 32;
-  for (int i = tid; i < TW; i += CT_BLOCK) { s_dxp[i] = k_dxp[i]; s_dyp[i] = k_dyp[i]; }
+  for (int i = tid; i < TW; i += CT_BLOCK) { s_dxp[i] = __ldg(a.dxp + i); s_dyp[i] = __ldg(a.dyp + i); }
   for (int i = tid; i < 511; i += CT_BLOCK) s_rb[i] = (double)(i - 255) / 255.0 + 0.5;
   for (int i = tid; i < CT_ZERO_BYTES / 4; i += CT_BLOCK) s_zero[i] = 0.0f;
   igi_fence_proxy_async();   // the zeros must be visible to the bulk-copy (async) proxy
   const bool three_lights = kc.n_lights == 3;   // the allsight yaml's light count: unrolled shading path
   (void)three_lights;
-  const float span_x0 = k_dxp[0], span_kx = (float)(TW - 1) / (k_dxp[TW - 1] - k_dxp[0]);
+  const float span_x0 = kc.sx0, span_kx = (float)(TW - 1) / (kc.sx1 - kc.sx0);
   // gel_depth = 0 of one frame (200 704 B of zeros): a few lanes of every warp hand 4 KB pieces of the zero
   // buffer to the bulk-copy engine (shared -> global), which costs this issue-bound kernel no store
   // instructions.  Every thread commits one (possibly empty) bulk group per call.
@@ -1083,8 +1093,8 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
               for (int u = 0; u < 2; ++u) {
                 const int px = xlo + u;
                 if (px <= xhi) {
-                  if (ex) raster_frag_depth(s.N, s.det, s.orig, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
-                  else raster_frag(s, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
+                  if (ex) raster_frag_depth(kc.znear, s.N, s.det, s.orig, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
+                  else raster_frag(kc.znear, s, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
                 }
               }
               xlo += 2;
@@ -1120,10 +1130,10 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
                   const uint4* q4 = reinterpret_cast<const uint4*>(list + kk);
                   const uint4 u2 = __ldg(q4 + 2), u3 = __ldg(q4 + 3);
                   const V3 N{__uint_as_float(u2.y), __uint_as_float(u2.z), __uint_as_float(u2.w)};
-                  raster_frag_depth(N, __uint_as_float(u3.x), u3.w, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
+                  raster_frag_depth(kc.znear, N, __uint_as_float(u3.x), u3.w, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
                 } else {
                   const Setup ss = load_setup(list + kk);
-                  raster_frag(ss, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
+                  raster_frag(kc.znear, ss, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
                 }
               }
             }
@@ -1170,9 +1180,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             V3 pp{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
 #if CT_SHADE_UNROLL
-            if (three_lights) shade_t<NCH, 3>(pp, n, rgb); else shade_t<NCH, 0>(pp, n, rgb);
+            if (three_lights) shade_t<NCH, 3>(kc, pp, n, rgb); else shade_t<NCH, 0>(kc, pp, n, rgb);
 #else
-            shade_t<NCH, 0>(pp, n, rgb);
+            shade_t<NCH, 0>(kc, pp, n, rgb);
 #endif
             const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
             // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
@@ -1348,12 +1358,12 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int sx0 = (ox >> 1) * 7 + ((ox & 1) ? 3 : 0), sy0 = (oy >> 1) * 7 + ((oy & 1) ? 3 : 0);
         double acc[3] = {0.0, 0.0, 0.0};
         for (int j = 0; j < 4; ++j) {
-          const float wy = (oy & 1) ? (j == 0 ? kc.area_w[1] : kc.area_w[0]) : (j == 3 ? kc.area_w[1] : kc.area_w[0]);
+          const float wy = (oy & 1) ? (j == 0 ? AREA_W1 : AREA_W0) : (j == 3 ? AREA_W1 : AREA_W0);
           const int fy = sy0 + j;           // flipped row
           const int py = TH - 1 - fy;       // original row
           double racc[3] = {0.0, 0.0, 0.0};
           for (int k = 0; k < 4; ++k) {
-            const float wx = (ox & 1) ? (k == 0 ? kc.area_w[1] : kc.area_w[0]) : (k == 3 ? kc.area_w[1] : kc.area_w[0]);
+            const float wx = (ox & 1) ? (k == 0 ? AREA_W1 : AREA_W0) : (k == 3 ? AREA_W1 : AREA_W0);
             const int px = sx0 + k;
             const int ddx = px - TW / 2, ddy = py - TH / 2;
             const double m = (ddx * ddx + ddy * ddy <= (TW / 2) * (TW / 2)) ? 1.0 : 0.0;  // circle_mask
@@ -1399,11 +1409,11 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
     const int sx0 = (ox >> 1) * 7 + ((ox & 1) ? 3 : 0), sy0 = (oy >> 1) * 7 + ((oy & 1) ? 3 : 0);
     double acc[3] = {0.0, 0.0, 0.0};
     for (int j = 0; j < 4; ++j) {
-      const float wy = (oy & 1) ? (j == 0 ? kc.area_w[1] : kc.area_w[0]) : (j == 3 ? kc.area_w[1] : kc.area_w[0]);
+      const float wy = (oy & 1) ? (j == 0 ? AREA_W1 : AREA_W0) : (j == 3 ? AREA_W1 : AREA_W0);
       const int py = TH - 1 - (sy0 + j);
       double racc[3] = {0.0, 0.0, 0.0};
       for (int k = 0; k < 4; ++k) {
-        const float wx = (ox & 1) ? (k == 0 ? kc.area_w[1] : kc.area_w[0]) : (k == 3 ? kc.area_w[1] : kc.area_w[0]);
+        const float wx = (ox & 1) ? (k == 0 ? AREA_W1 : AREA_W0) : (k == 3 ? AREA_W1 : AREA_W0);
         const int px = sx0 + k;
         const int ddx = px - TW / 2, ddy = py - TH / 2;
         const double m = (ddx * ddx + ddy * ddy <= (TW / 2) * (TW / 2)) ? 1.0 : 0.0;
@@ -1424,44 +1434,19 @@ __global__ void tac_obs_kernel(const uint8_t* __restrict__ color, const uint8_t*
 // =============================================================================================
 // C-ABI
 // =============================================================================================
-static int g_gray = 0;  // mirrors kc.gray of the last igi_tactile_set_sensor (one device per process)
-static int g_region_budget = 0;  // 0 = compiled budget
 #ifndef FILL_GEOM_PARTS
-#define FILL_GEOM_PARTS 5
+#define FILL_GEOM_PARTS 5   // fill parts (1 colour, 2 gel_depth, 4 obs) written by tac_geom; the rest by tac_contact
 #endif
-static int g_fill_geom_parts = FILL_GEOM_PARTS;  // fill parts (1 colour, 2 gel_depth, 4 obs) written by tac_geom; the rest by tac_contact
 
-extern "C" int igi_tactile_set_fill_split(int geom_parts) {
-  IGI_REQUIRE(geom_parts >= 0 && geom_parts <= 7, "igi_tactile_set_fill_split: parts mask must be 0..7");
-  g_fill_geom_parts = geom_parts;
-  return IGI_OK;
-}
-
-static int g_fill_prefilled_parts = 0;  // fill parts the caller wrote itself before the call (neither kernel writes them)
-
-extern "C" int igi_tactile_set_prefilled(int parts) {
-  IGI_REQUIRE(parts >= 0 && parts <= 7, "igi_tactile_set_prefilled: parts mask must be 0..7");
-  g_fill_prefilled_parts = parts;
-  return IGI_OK;
-}
-
-extern "C" int igi_memset_async(void* dst, int value, unsigned long long bytes, void* stream) {
-  IGI_REQUIRE(dst != nullptr, "igi_memset_async: null pointer");
-  IGI_CUDA(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
-  return IGI_OK;
-}
-
-extern "C" int igi_tactile_set_region_budget(int pixels) {
-  IGI_REQUIRE(pixels == 0 || pixels >= (2 * HALO + 1) * (2 * HALO + 1), "igi_tactile_set_region_budget: need 0 or >= 49 pixels");
-  g_region_budget = pixels;
-  return IGI_OK;
-}
-
-extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
-  IGI_REQUIRE(p != nullptr, "igi_tactile_set_sensor: null params");
-  IGI_REQUIRE(p->width == TW && p->height == TH, "igi_tactile_set_sensor: only 224x224 is built");
-  IGI_REQUIRE(p->n_lights >= 0 && p->n_lights <= MAX_LIGHTS, "igi_tactile_set_sensor: at most 8 lights");
-  IGI_REQUIRE(p->blur_ksize == 7, "igi_tactile_set_sensor: blur kernel size must be 7");
+// IgiSensorParams (host) -> the constant block every launch carries.  No library state: two engines with
+// different sensor yamls, or on different devices, never see each other's constants.
+static int make_const(const IgiSensorParams* p, TacConst* out) {
+  IGI_REQUIRE(p != nullptr, "sensor params: null");
+  IGI_REQUIRE(p->width == TW && p->height == TH, "sensor params: only 224x224 is built");
+  IGI_REQUIRE(p->n_lights >= 0 && p->n_lights <= MAX_LIGHTS, "sensor params: at most 8 lights");
+  IGI_REQUIRE(p->blur_ksize == 7, "sensor params: blur kernel size must be 7");
+  IGI_REQUIRE(p->n_lights == 0 || (p->light_pos && p->light_dir && p->light_col && p->light_int && p->light_las && p->light_lao),
+              "sensor params: null light array");
   TacConst c{};
   c.znear = p->znear;
   c.n_lights = p->n_lights;
@@ -1497,7 +1482,6 @@ extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
         gray = gray && p->light_col[3 * i + k] == p->light_col[3 * i];
       }
     c.gray = gray ? 1 : 0;
-    g_gray = c.gray;
   }
   for (int k = 0; k < 9; ++k) c.cam_R[k] = p->cam_R[k];
   for (int k = 0; k < 3; ++k) c.cam_p[k] = p->cam_p[k];
@@ -1512,38 +1496,41 @@ extern "C" int igi_tactile_set_sensor(const IgiSensorParams* p) {
   c.grid_h = p->grid_h;
   c.grid_slack = p->grid_slack;
   c.depth0_max = p->depth0_max;
-  IGI_REQUIRE(p->hiz_levels >= 1 && p->hiz_levels <= 10, "igi_tactile_set_sensor: hiz_levels must be 1..10");
+  IGI_REQUIRE(p->hiz_levels >= 1 && p->hiz_levels <= 10, "sensor params: hiz_levels must be 1..10");
   c.hiz_levels = p->hiz_levels;
   for (int k = 0; k < p->hiz_levels; ++k) { c.hiz_off[k] = p->hiz_off[k]; c.hiz_w[k] = p->hiz_w[k]; }
-  c.area_w[0] = p->area_w_full;
-  c.area_w[1] = p->area_w_half;
-  IGI_CUDA(cudaMemcpyToSymbol(kc, &c, sizeof(c)));
-  IGI_CUDA(cudaMemcpyToSymbol(k_dxp, p->dxp, sizeof(float) * TW));
-  IGI_CUDA(cudaMemcpyToSymbol(k_dyp, p->dyp, sizeof(float) * TH));
+  c.sx0 = p->dxp_first; c.sx1 = p->dxp_last; c.sy0 = p->dyp_first; c.sy1 = p->dyp_last;
+  IGI_REQUIRE(c.sx1 != c.sx0 && c.sy1 != c.sy0, "sensor params: degenerate ray-slope range");
+  *out = c;
   return IGI_OK;
 }
 
-extern "C" int igi_tactile_gel_precompute(const float* gel_tris, int n_tris, uint64_t* scratch_zbuf,
-                                          float* depth0, uint8_t* bg_sim, void* stream) {
-  IGI_REQUIRE(gel_tris && scratch_zbuf && depth0 && bg_sim && n_tris > 0, "igi_tactile_gel_precompute: bad args");
+extern "C" int igi_tactile_gel_precompute(const IgiSensorParams* sensor, const float* dxp, const float* dyp,
+                                          const float* gel_tris, int n_tris, uint64_t* scratch_zbuf, float* depth0,
+                                          uint8_t* bg_sim, void* stream) {
+  IGI_REQUIRE(dxp && dyp && gel_tris && scratch_zbuf && depth0 && bg_sim && n_tris > 0, "igi_tactile_gel_precompute: bad args");
+  TacConst kc;
+  const int rc = make_const(sensor, &kc);
+  if (rc != IGI_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   IGI_CUDA(cudaMemsetAsync(scratch_zbuf, 0xff, sizeof(uint64_t) * TW * TH, s));
-  tac_gel_raster<<<(n_tris + 127) / 128, 128, 0, s>>>(gel_tris, n_tris, (unsigned long long*)scratch_zbuf);
+  tac_gel_raster<<<(n_tris + 127) / 128, 128, 0, s>>>(kc, dxp, dyp, gel_tris, n_tris, (unsigned long long*)scratch_zbuf);
   IGI_CHECK_LAUNCH("tac_gel_raster");
-  tac_gel_shade<<<(TW * TH + 255) / 256, 256, 0, s>>>(gel_tris, (const unsigned long long*)scratch_zbuf, depth0, bg_sim);
+  tac_gel_shade<<<(TW * TH + 255) / 256, 256, 0, s>>>(kc, dxp, dyp, gel_tris, (const unsigned long long*)scratch_zbuf, depth0, bg_sim);
   IGI_CHECK_LAUNCH("tac_gel_shade");
   return IGI_OK;
 }
 
-extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileStatic* st, const IgiTactileFrames* fr,
-                                  const IgiTactileScratch* sc, const IgiTactileOut* out, void* stream) {
-  IGI_REQUIRE(m && st && fr && sc && out, "igi_tactile_render: null struct");
+extern "C" int igi_tactile_render(const IgiSensorParams* sensor, const IgiTactileMeshes* m, const IgiTactileStatic* st,
+                                  const IgiTactileFrames* fr, const IgiTactileScratch* sc, const IgiTactileOut* out,
+                                  void* stream) {
+  IGI_REQUIRE(sensor && m && st && fr && sc && out, "igi_tactile_render: null struct");
   IGI_REQUIRE(fr->n_envs >= 0 && fr->sensors_per_env >= 1, "igi_tactile_render: bad frame counts");
   IGI_REQUIRE(fr->finger_pos && fr->finger_quat && fr->plug_pos && fr->plug_quat && fr->mesh_id && fr->bg_id,
               "igi_tactile_render: null pose pointer");
   IGI_REQUIRE(m->verts && m->vnorm && m->faces && m->face_orig && m->meshes && m->clusters,
               "igi_tactile_render: null mesh pointer");
-  IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid && st->hiz,
+  IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid && st->hiz && st->dxp && st->dyp,
               "igi_tactile_render: null static pointer");
   IGI_REQUIRE(sc->normals, "igi_tactile_render: scratch.normals is null ((F,kmax) 48-byte records)");
   IGI_REQUIRE(sc->M && sc->setups && sc->counts && sc->bbox && sc->worklist && sc->counters && sc->kmax > 0 &&
@@ -1554,6 +1541,14 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
                   out->obs_env_stride % 4 == 0 && out->obs_sensor_stride % 4 == 0,
               "igi_tactile_render: bad obs output strides");
   IGI_REQUIRE(out->color && out->gel_depth, "igi_tactile_render: color and gel_depth outputs are required");
+  IGI_REQUIRE(fr->fill_split >= 0 && fr->fill_split <= 8, "igi_tactile_render: fill_split must be 0 (default) or parts mask + 1");
+  IGI_REQUIRE(fr->region_budget == 0 || fr->region_budget >= (2 * HALO + 1) * (2 * HALO + 1),
+              "igi_tactile_render: region_budget must be 0 or >= 49 pixels");
+  TacConst kc;
+  {
+    const int rc = make_const(sensor, &kc);
+    if (rc != IGI_OK) return rc;
+  }
   const int F = fr->n_envs * fr->sensors_per_env;
   if (F == 0) return IGI_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1563,11 +1558,12 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   IGI_REQUIRE((stages & ~15) == 0 && !((stages & 8) && (stages & 3)),
               "igi_tactile_render: stage_mask 8 (fused geometry+fill) excludes bits 1 and 2");
   // In the fused modes (no bit 1 / 2) the fill is split between the two kernels: tac_geom writes
-  // g_fill_geom_parts, tac_contact the rest (it then visits every live frame, not only those with candidates).
+  // fill_geom_parts, tac_contact the rest (it then visits every live frame, not only those with candidates).
   const bool fused = (stages & 3) == 0;
-  const int parts_geom = fused ? (g_fill_geom_parts & ~g_fill_prefilled_parts) : 0,
-            parts_contact = fused ? (7 & ~g_fill_geom_parts & ~g_fill_prefilled_parts) : 0;
-  // counters: [0] work_n, [1] cursor, [2] overflow (sticky; the caller reads and clears it)
+  const int fill_geom_parts = fr->fill_split ? fr->fill_split - 1 : FILL_GEOM_PARTS;
+  const int parts_geom = fused ? fill_geom_parts : 0, parts_contact = fused ? (7 & ~fill_geom_parts) : 0;
+  // counters: [0] work_n, [1] cursor, [2] overflow (sticky), [3] largest triangle count of a frame (sticky);
+  // the caller reads [2], [3] whenever it likes (e.g. an asynchronous copy per step) and clears them
   if (stages & 9) IGI_CUDA(cudaMemsetAsync(sc->counters, 0, 2 * sizeof(int32_t), s));
   else IGI_CUDA(cudaMemsetAsync(sc->counters + 1, 0, sizeof(int32_t), s));
   FillArgs fa{};
@@ -1582,6 +1578,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
   g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
   g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz; g.depth0 = st->depth0;
+  g.dxp = st->dxp; g.dyp = st->dyp;
   g.M_out = sc->M; g.setups = (Setup*)sc->setups; g.vnorm = m->vnorm; g.nrecs = (NRec*)sc->normals; g.counts = sc->counts; g.bbox = sc->bbox;
   g.worklist = sc->worklist; g.work_n = sc->counters; g.overflow = sc->counters + 2;
   g.sensors_per_env = fr->sensors_per_env; g.kmax = sc->kmax; g.force_const = fr->force_const;
@@ -1590,7 +1587,7 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   g.fill = fa;
   g.fill.parts = parts_geom;
   if (stages & 9) {
-    tac_geom<<<F, GEOM_BLOCK, 0, s>>>(g);
+    tac_geom<<<F, GEOM_BLOCK, 0, s>>>(kc, g);
     IGI_CHECK_LAUNCH("tac_geom");
   }
   if (stages & 2) {
@@ -1601,46 +1598,49 @@ extern "C" int igi_tactile_render(const IgiTactileMeshes* m, const IgiTactileSta
   ca.M = sc->M; ca.setups = (const Setup*)sc->setups; ca.nrecs = (const NRec*)sc->normals; ca.counts = sc->counts; ca.bbox = sc->bbox;
   ca.worklist = sc->worklist; ca.work_n = sc->counters; ca.cursor = sc->counters + 1;
   ca.verts = m->verts; ca.vnorm = m->vnorm; ca.faces = m->faces;
-  ca.depth0 = st->depth0; ca.hiz = st->hiz; ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
+  ca.depth0 = st->depth0; ca.hiz = st->hiz; ca.dxp = st->dxp; ca.dyp = st->dyp;
+  ca.bg_sim = st->bg_sim; ca.bg_real = st->bg_real; ca.bg_id = fr->bg_id;
   ca.color = out->color; ca.gel_depth = out->gel_depth; ca.obs = out->obs;
   ca.obs_env_stride = out->obs_env_stride; ca.obs_sensor_stride = out->obs_sensor_stride;
   ca.sensors_per_env = fr->sensors_per_env;
   ca.kmax = sc->kmax;
   ca.fill = fa;
   ca.fill.parts = parts_contact;
+  const bool gray = kc.gray != 0;
   {
-    const int compiled = g_gray ? CT_BUD_GRAY : CT_BUD_RGB;
-    ca.budget = g_region_budget > 0 && g_region_budget < compiled ? g_region_budget : compiled;
+    const int compiled = gray ? CT_BUD_GRAY : CT_BUD_RGB;
+    ca.budget = fr->region_budget > 0 && fr->region_budget < compiled ? fr->region_budget : compiled;
   }
   int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  IGI_CUDA(cudaGetDevice(&dev));
+  IGI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (stages & 4) {
     constexpr size_t smem_gray = (size_t)CT_BUD_GRAY * 8, smem_rgb = (size_t)CT_BUD_RGB * (8 + 24);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-DEVICE function attribute
+    static bool attr_set[64] = {false};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       IGI_CUDA(cudaFuncSetAttribute(tac_contact<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gray));
       IGI_CUDA(cudaFuncSetAttribute(tac_contact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rgb));
-      attr_set = true;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
 #if CT_PDL
     {
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(g_gray ? min(F, sms * CT_CTAS) : min(F, sms)));
+      cfg.gridDim = dim3((unsigned)(gray ? min(F, sms * CT_CTAS) : min(F, sms)));
       cfg.blockDim = dim3(CT_BLOCK);
-      cfg.dynamicSmemBytes = g_gray ? smem_gray : smem_rgb;
+      cfg.dynamicSmemBytes = gray ? smem_gray : smem_rgb;
       cfg.stream = s;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[0].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      if (g_gray) IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<1>, ca));
-      else IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<3>, ca));
+      if (gray) IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<1>, kc, ca));
+      else IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<3>, kc, ca));
     }
 #else
-    if (g_gray) tac_contact<1><<<min(F, sms * CT_CTAS), CT_BLOCK, smem_gray, s>>>(ca);
-    else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(ca);
+    if (gray) tac_contact<1><<<min(F, sms * CT_CTAS), CT_BLOCK, smem_gray, s>>>(kc, ca);
+    else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(kc, ca);
 #endif
     IGI_CHECK_LAUNCH("tac_contact");
   }

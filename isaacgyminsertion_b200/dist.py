@@ -6,6 +6,7 @@ The reference exchanges no observations (each rank trains on its own envs,
 isaacgyminsertion/train.py:58-64; ext_adapt.py:172-178 only all-reduces gradients), so
 this is the glue the north star adds, not a replacement of reference code.
 """
+import ctypes
 import os
 
 import torch
@@ -58,3 +59,229 @@ def gather_observations(obs_packed, total_envs=None, out=None):
         lo, hi = env_slice(total_envs, r, world)
         parts.append(buf[r * n_max: r * n_max + (hi - lo)])
     return torch.cat(parts, dim=0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# per-step gather object: NCCL all-gather, or copy-engine peer copies into the learner's buffer
+# ---------------------------------------------------------------------------------------------------
+class _DevMem:
+    """Raw device block as a __cuda_array_interface__ object (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _view(ptr, nbytes, device, dtype, shape):
+    return torch.as_tensor(_DevMem(ptr, nbytes), device=device).view(dtype).view(shape)
+
+
+class ObsGather:
+    """One gather of the packed observation rows per env step.
+
+    transport="nccl": `all_gather_into_tensor` on a side stream (every rank receives every row; the
+        learner reads rank `learner`'s copy).  NCCL's copy kernels need SMs, which tac_contact's persistent
+        CTAs own for most of a step.
+    transport="p2p": every rank copies its rows straight into the LEARNER's buffer (one cudaMalloc block
+        exported over CUDA IPC) with a copy-engine peer copy over NVLink and publishes the step number with
+        a second 4-byte copy; the learner's stream waits for the step number of every rank with a stream
+        memory operation (`cuStreamWaitValue32`), peers wait for the learner's "consumed" word the same way
+        before they overwrite a slot.  No kernel, no SM, 1/world of the all-gather's traffic.
+
+    gather(obs) enqueues this step's transfer behind the work already on the current stream and returns a
+    ticket; wait(ticket) makes the current stream wait for it and returns the (total_envs, row) tensor on the
+    learner (None on the other ranks with "p2p").  The tensor stays valid until the next gather() call.
+    """
+
+    def __init__(self, obs_like, total_envs=None, transport="p2p", learner=0, slots=2):
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.device = obs_like.device
+        self.rows, self.row = obs_like.shape
+        self.total = int(total_envs) if total_envs is not None else self.rows * self.world
+        self.transport = transport if self.world > 1 else "none"
+        self.learner, self.slots = int(learner), max(int(slots), 2)
+        self.lo, self.hi = env_slice(self.total, self.rank, self.world)
+        if self.hi - self.lo != self.rows:
+            raise RuntimeError(f"rank {self.rank} owns envs [{self.lo},{self.hi}) but obs has {self.rows} rows")
+        self.step = 0
+        self.bytes_per_step = self.rows * self.row * 4
+        self.comm_ms = None
+        if self.transport == "none":
+            return
+        if self.device.type == "cuda":
+            self.stream = torch.cuda.Stream(device=self.device)
+            self._ev_ready = torch.cuda.Event()
+        if self.transport == "nccl":
+            self._out = [torch.empty((self.total, self.row), dtype=torch.float32, device=self.device)
+                         for _ in range(self.slots)]
+            self._send = [torch.empty((self.rows, self.row), dtype=torch.float32, device=self.device)
+                          for _ in range(self.slots)] if self.total % self.world == 0 else None
+            self._work = None
+        elif self.transport == "p2p":
+            self._init_p2p()
+        else:
+            raise ValueError(f"unknown transport {transport!r}")
+
+    # ---- p2p setup --------------------------------------------------------------------------------
+    def _init_p2p(self):
+        from . import _lib
+        self.lib = lib = _lib.load()
+        self._check = _lib.check
+        c = ctypes
+        is_learner = self.rank == self.learner
+        slot_bytes = self.total * self.row * 4
+        # learner: data slots + one "arrived" word per rank (padded to 256 B);  everyone: a "consumed" word + staging
+        my_bytes = (self.slots * slot_bytes + 256 * self.world) if is_learner else 0
+        my_bytes += 1024
+        ptr, handle = c.c_void_p(), (c.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            self._check(lib.igi_peer_alloc(c.c_ulonglong(my_bytes), c.byref(ptr), handle), "igi_peer_alloc")
+        self._own = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        # control words at the END of every rank's block: [consumed | staging_a | staging_b]
+        self._ctl = self._own + my_bytes - 1024
+        self._mapped = {}
+        if is_learner:
+            self._data = self._own
+            self._arrived = self._own + self.slots * slot_bytes
+            self._peer_ctl = {}
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = c.c_void_p()
+                h = (c.c_ubyte * 64).from_buffer_copy(handles[r])
+                with torch.cuda.device(self.device):
+                    self._check(lib.igi_peer_open(h, c.byref(p)), "igi_peer_open")
+                self._mapped[r] = p.value
+                self._peer_ctl[r] = p.value            # a non-learner block is just its control words
+            self._slot_views = [_view(self._data + i * slot_bytes, slot_bytes, self.device, torch.float32,
+                                      (self.total, self.row)) for i in range(self.slots)]
+            self._ev_done = torch.cuda.Event()
+            self._ev_t0 = torch.cuda.Event(enable_timing=True)
+            self._ev_t1 = torch.cuda.Event(enable_timing=True)
+        else:
+            p = c.c_void_p()
+            h = (c.c_ubyte * 64).from_buffer_copy(handles[self.learner])
+            with torch.cuda.device(self.device):
+                self._check(lib.igi_peer_open(h, c.byref(p)), "igi_peer_open")
+            self._mapped[self.learner] = p.value
+            self._data = p.value
+            self._arrived = p.value + self.slots * slot_bytes
+        self._slot_bytes = slot_bytes
+        self._ev_read = torch.cuda.Event()
+        dist.barrier()
+
+    # ---- per step ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def gather(self, obs):
+        if self.transport == "none":
+            return obs
+        self.step += 1
+        s, slot = self.step, self.step % self.slots
+        cur = torch.cuda.current_stream(self.device)
+        if self.transport == "nccl":
+            if self._work is not None:
+                self._work.wait()
+            if self._send is None:          # ragged slices: padded gather
+                self._ev_ready.record(cur)
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(self._ev_ready)
+                    out = gather_observations(obs, self.total)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                return ("nccl", out, ev)
+            buf = self._send[slot]
+            buf.copy_(obs)                  # snapshot: the kernels of the next step rewrite obs while NCCL reads
+            self._ev_ready.record(cur)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(self._ev_ready)
+                self._work = dist.all_gather_into_tensor(self._out[slot], buf, async_op=True)
+            return ("nccl", self._out[slot], self._work)
+        # ---- p2p
+        if obs.shape != (self.rows, self.row) or not obs.is_contiguous() or obs.dtype != torch.float32:
+            raise RuntimeError("ObsGather: obs must be the contiguous (rows, row) f32 tensor given at construction")
+        c, lib = ctypes, self.lib
+        st = c.c_void_p(self.stream.cuda_stream)
+        is_learner = self.rank == self.learner
+        self._ev_ready.record(cur)                      # obs rows of this step are complete behind this point
+        self.stream.wait_event(self._ev_ready)
+        with torch.cuda.device(self.device):
+            if is_learner:
+                # everything the caller enqueued so far may still read the slot of step s - slots + 1 ... the
+                # result of step s-1 is declared consumed now (contract: valid until the next gather call)
+                if s > 1:
+                    self._check(lib.igi_stream_write_value32(st, c.c_void_p(self._ctl + 4), c.c_uint(s - 1)),
+                                "igi_stream_write_value32")
+                    for r, pctl in self._peer_ctl.items():
+                        self._check(lib.igi_peer_copy_async(c.c_void_p(pctl), c.c_void_p(self._ctl + 4),
+                                                            c.c_ulonglong(4), st), "igi_peer_copy_async")
+                self._ev_t0.record(self.stream)
+            elif s - self.slots >= 1:
+                # the slot of step s was last used by step s - slots: wait until the learner consumed that step
+                self._check(lib.igi_stream_wait_value32_geq(st, c.c_void_p(self._ctl), c.c_uint(s - self.slots)),
+                            "igi_stream_wait_value32_geq")
+            dst = self._data + slot * self._slot_bytes + self.lo * self.row * 4
+            self._check(lib.igi_peer_copy_async(c.c_void_p(dst), c.c_void_p(obs.data_ptr()),
+                                                c.c_ulonglong(self.bytes_per_step), st), "igi_peer_copy_async")
+            arrived = self._arrived + 256 * self.rank
+            if is_learner:
+                self._check(lib.igi_stream_write_value32(st, c.c_void_p(arrived), c.c_uint(s)),
+                            "igi_stream_write_value32")
+                for r in range(self.world):
+                    if r != self.rank:
+                        self._check(lib.igi_stream_wait_value32_geq(st, c.c_void_p(self._arrived + 256 * r),
+                                                                    c.c_uint(s)), "igi_stream_wait_value32_geq")
+                self._ev_t1.record(self.stream)
+            else:
+                self._check(lib.igi_stream_write_value32(st, c.c_void_p(self._ctl + 8), c.c_uint(s)),
+                            "igi_stream_write_value32")
+                self._check(lib.igi_peer_copy_async(c.c_void_p(arrived), c.c_void_p(self._ctl + 8),
+                                                    c.c_ulonglong(4), st), "igi_peer_copy_async")
+        # obs may be rewritten by the next step's kernels once the copy has read it
+        self._ev_read.record(self.stream)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ("p2p", self._slot_views[slot] if is_learner else None, ev)
+
+    def wait(self, ticket):
+        """Current stream waits for the ticket's transfer; returns the gathered tensor (learner) or None."""
+        if self.transport == "none":
+            return ticket
+        kind, out, h = ticket
+        cur = torch.cuda.current_stream(self.device)
+        if kind == "nccl" and not isinstance(h, torch.cuda.Event):
+            h.wait()
+            cur.wait_stream(self.stream)
+        else:
+            cur.wait_event(h)
+        return out
+
+    def protect_source(self):
+        """Current stream waits until the last gather() has READ its source rows (call before rewriting obs)."""
+        if self.transport == "p2p" and self.step > 0:
+            torch.cuda.current_stream(self.device).wait_event(self._ev_read)
+
+    def last_comm_ms(self):
+        """Learner, p2p: device time from 'own rows ready' to 'every rank's rows arrived' of the last step."""
+        if self.transport == "p2p" and self.rank == self.learner and self.step > 0:
+            self._ev_t1.synchronize()
+            return self._ev_t0.elapsed_time(self._ev_t1)
+        return None
+
+    def close(self):
+        if self.transport == "nccl" and self._work is not None:
+            self._work.wait()
+        if self.transport != "p2p":
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        with torch.cuda.device(self.device):
+            for p in self._mapped.values():
+                self.lib.igi_peer_close(ctypes.c_void_p(p))
+            self._mapped = {}
+            dist.barrier()
+            self._slot_views = None
+            self.lib.igi_peer_free(ctypes.c_void_p(self._own))
+        self.transport = "none"

@@ -156,6 +156,9 @@ class BatchedPointCloud:
         self.e2g_inv = e2g.reshape(n, 16).to(self.device).contiguous()
         self._scratch = {}
         self.rng_stream = TorchCpuRandintStream()
+        # True when this engine holds one rank's contiguous env slice of a larger job (torch.distributed
+        # initialised): the reference sampler then takes its index words by GLOBAL env order.
+        self.sharded = False
 
     # -- scratch ---------------------------------------------------------------
     def _buf(self, name, shape, dtype):
@@ -210,8 +213,22 @@ class BatchedPointCloud:
         if out is None:
             out = torch.empty((n, m, 3), dtype=torch.float32, device=self.device)
         assert out.stride(-1) == 1 and out.stride(-2) == 3
-        raw_np = self.rng_stream.peek(n * m)
-        raw = torch.from_numpy(raw_np.view(np.int32)).to(self.device, non_blocking=False)
+        skip = total_words = 0
+        if self.sharded:
+            # The reference draws m words per NON-EMPTY env in global env order (pcl_utils.py:178-183), so a rank
+            # starts m x (non-empty envs on lower ranks) words into the stream and the call consumes m x (non-empty
+            # envs of the whole job).  Every rank's CPU generator must be in the same state (same torch.manual_seed),
+            # as it is in the single-process run.  One tiny all-gather + host read: this sampler is host-synchronous
+            # by construction (its indices come from the CPU generator).
+            import torch.distributed as dist
+            mine = (any_[:, cls] != 0).sum().to(torch.int64).reshape(1)
+            every = torch.empty(dist.get_world_size(), dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(every, mine)
+            every = every.cpu().tolist()
+            skip = m * int(sum(every[:dist.get_rank()]))
+            total_words = m * int(sum(every))
+        raw_np = self.rng_stream.peek(skip + n * m)[skip:]
+        raw = torch.from_numpy(raw_np.view(np.int32).copy()).to(self.device, non_blocking=False)
         idx = torch.empty((n, m), dtype=torch.int32, device=self.device) if return_idx else None
         consumed = self._buf("consumed", (1,), torch.int32)
         offs = self._buf("offs", (n,), torch.int32)
@@ -222,12 +239,12 @@ class BatchedPointCloud:
             _lib.dptr(offs), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_pcl_sample_gather")
         if strict_rng:
-            self.rng_stream.commit(int(consumed.item()))
+            self.rng_stream.commit(total_words if self.sharded else int(consumed.item()))
         return (out, idx) if return_idx else out
 
     # -- K5B ---------------------------------------------------------------------
     @torch.no_grad()
-    def sample_fps(self, pts, cnt, any_, cls, m, out=None, return_idx=False):
+    def sample_fps(self, pts, cnt, any_, cls, m, out=None, return_idx=False, flags=0):
         """FPS of class `cls` (int) or of every class at once (cls=None: out is (n, C, m, 3)).
         Size-ordered schedule (igi_fps_balanced)."""
         n, C, cap, _ = pts.shape
@@ -251,7 +268,7 @@ class BatchedPointCloud:
             _c.c_void_p(p0.data_ptr()), _c.c_int64(task_stride),
             _c.c_void_p(c0.data_ptr()), _c.c_void_p(a0.data_ptr()), _c.c_int64(count_stride),
             _c.c_int(n_tasks), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out_stride),
-            _lib.dptr(idx), _lib.dptr(scratch), _lib.stream_ptr(self.device))
+            _lib.dptr(idx), _lib.dptr(scratch), _c.c_int(flags), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_fps_balanced")
         return (out, idx) if return_idx else out
 
@@ -268,13 +285,13 @@ class BatchedPointCloud:
             _c.c_void_p(p0.data_ptr()), _c.c_int64(pts.stride(0)),
             _c.c_void_p(cnt[:, cls].data_ptr()), _c.c_void_p(any_[:, cls].data_ptr()), _c.c_int64(C),
             _c.c_int(0), _c.c_int(n), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out.stride(0)),
-            _lib.dptr(idx), _lib.stream_ptr(self.device))
+            _lib.dptr(idx), _c.c_int(0), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_fps")
         return (out, idx) if return_idx else out
 
 
 @torch.no_grad()
-def furthest_point_sample(xyz, npoint):
+def furthest_point_sample(xyz, npoint, flags=0):
     """pointnet2_ops.pointnet2_utils.furthest_point_sample(xyz (B,N,3) f32 cuda, npoint) -> (B,npoint) i32
     (the call behind `fps()` in algo/models/transformer/point_mae.py:14-21)."""
     lib = _lib.load()
@@ -283,7 +300,7 @@ def furthest_point_sample(xyz, npoint):
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
     rc = lib.igi_fps(_lib.dptr(xyz, torch.float32, "xyz"), _c.c_int64(N * 3), None, None, _c.c_int64(1),
                      _c.c_int(N), _c.c_int(B), _c.c_int(npoint), None, _c.c_int64(npoint * 3),
-                     _lib.dptr(idx), _lib.stream_ptr(xyz.device))
+                     _lib.dptr(idx), _c.c_int(flags), _lib.stream_ptr(xyz.device))
     _lib.check(rc, "igi_fps")
     return idx
 
@@ -407,7 +424,13 @@ class CameraPointCloud:
 
     @torch.no_grad()
     def _proc_pts(self, env_id, depth_images, filter_func=None):
-        return self.get_ptd_cuda(depth_images.unsqueeze(0), env_ids=[env_id], filter_func=filter_func)[0]
+        """pcl_utils.py:186-193: ONE env's depth image (H,W) with that env's camera -> (M,3)."""
+        if filter_func is None:
+            filter_func = self.filter_func
+        box = _box_of(filter_func)
+        d = depth_images.to(self.graphics_device).reshape(1, -1).contiguous().float()
+        pts, cnt, _ = self.engine.compact(d, None, (0,), box, env_ids=[int(env_id)])
+        return pts[0, 0, :int(cnt[0, 0].item())].clone()
 
     @torch.no_grad()
     def sample_n(self, pts, sample_num=None):

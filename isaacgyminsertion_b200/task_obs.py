@@ -51,11 +51,15 @@ class PointCloudAugmentations:
 
 class FactoryTaskInsertionTactileObs:
     def __init__(self, num_envs, gym, mesh_ids, bg_ids=None, device="cuda", num_points=400, num_points_socket=400,
-                 tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=2048,
+                 tact_hist_len=1, pcl_hist_len=1, sampler="reference", tactile=True, pcl_cam=True, kmax=1024,
                  strict_rng=True, pcl_noise_enabled=False, overlap_streams=True, include_all_pcl=False,
-                 total_points=2048, prefill_gel_depth=False):
+                 total_points=2048, falloff=None, global_env_offset=0, total_envs=None):
         self.device = torch.device(device)
         self.num_envs = num_envs
+        # env sharding: this object owns global envs [global_env_offset, global_env_offset + num_envs)
+        # of a job of total_envs; results do not depend on how the envs are sharded
+        self.global_env_offset = int(global_env_offset)
+        self.total_envs = int(total_envs) if total_envs is not None else int(num_envs)
         self.fingertips = ["finger_1_3", "finger_2_3", "finger_3_3"]   # factory_env_insertion.py:748
         self.num_points, self.num_points_socket = num_points, num_points_socket
         # pcl row = [plug | socket | all-scene] (pcl_components order, factory_task_insertion.py:1014-1027);
@@ -89,18 +93,19 @@ class FactoryTaskInsertionTactileObs:
         self.rot_pcl_angle = torch.zeros(N, device=dev)
         self.rot_axes = torch.zeros(N, dtype=torch.long, device=dev)
         self.pcl_process = PointCloudAugmentations(num_points=num_points)
+        self.pcl_rot = 30.0                # cfg_task.randomize.pcl_rot, degrees (FactoryTaskInsertionTactile.yaml:154)
         self.res = [gym.width, gym.height]
         self.seg_buf = torch.zeros(N, self.res[1] * self.res[0], dtype=torch.int32, device=dev)
         self.tactile = tactile
         self.pcl_cam = pcl_cam
         if tactile:
-            self.tactile_engine = BatchedAllSight(N, mesh_ids, bg_ids, device=dev, kmax=kmax,
-                                                  prefill_gel_depth=prefill_gel_depth)
+            self.tactile_engine = BatchedAllSight(N, mesh_ids, bg_ids, device=dev, kmax=kmax, falloff=falloff)
             self.tactile_handles = None    # built lazily by `handles()`
         if pcl_cam:
             self.pcl_generator = CameraPointCloud(None, gym, gym.envs, gym.camera_handles, gym.camera_props,
                                                   sample_num=num_points, filter_func=filter_pts, pt_in_local=True,
                                                   graphics_device=dev, compute_device=dev, sampler=sampler)
+            self.pcl_generator.engine.sharded = self.total_envs != self.num_envs
             self._plug_pts = (self._both_pts[:, 0] if self._both_pts is not None else
                               torch.zeros((N, num_points, 3), dtype=torch.float32, device=dev))
         # state the reference reads from gym tensors
@@ -241,11 +246,26 @@ class FactoryTaskInsertionTactileObs:
 
     # ------------------------------------------------------------------ reset / obs
     def reset_idx(self, env_ids):
-        """Observation part of the reset (factory_task_insertion.py:1753-1777)."""
-        self.tactile_queue[env_ids] = 0
-        self.pcl_queue[env_ids] = 0
-        self.got_socket[env_ids] = 0
-        self._socket_pending = True
+        """Observation part of the reset (factory_task_insertion.py:1753-1777): queues AND the current
+        buffers of the reset envs are zeroed, so an env whose update flag is off on the next step shows
+        zeros (the reference copies `tactile_queue[e, 0]`, which is 0 after a reset, :578-579), and the
+        per-env point-cloud augmentation state is redrawn with the reference's three calls in its order
+        (CPU generator: uniform angles; CUDA generator: position noise, rotation axes)."""
+        if self.tactile:
+            self.tactile_queue[env_ids] = 0
+            self.tactile_imgs[env_ids] = 0.
+        self.seg_buf[env_ids] = 0
+        if self.pcl_cam:
+            N, dev = self.num_envs, self.device
+            rand_angles = torch.FloatTensor(N).uniform_(-self.pcl_rot, self.pcl_rot).to(dev)
+            self.rot_pcl_angle[env_ids] = torch.deg2rad(rand_angles)[env_ids]
+            self.pcl_pos_noise[env_ids] = torch.randn(N, 1, 3, device=dev)[env_ids]
+            self.rot_axes[env_ids] = torch.randint(0, 3, (N,), device=dev)[env_ids]
+            self.pcl_queue[env_ids] = 0
+            self.pcl[env_ids] = 0
+            self.got_socket[env_ids] = 0
+            self.socket_pcl[env_ids] = 0
+            self._socket_pending = True
 
     def obs_dict(self, rl_device=None):
         """factory_task_insertion.py:2126-2144."""

@@ -41,7 +41,7 @@ typedef struct {
   const float* light_lao; /* (L) spot angle offset */
   float base[3];
   float metallic, roughness;
-  int inverse_square; /* 1: attenuate by 1/d^2 (pyrender as remembered); 0: no distance falloff (sensor yaml `lights.falloff`) */
+  int inverse_square; /* 1: attenuate by 1/d^2 (pyrender's documented punctual-light model, the default); 0: no distance falloff (sensor yaml `lights.falloff: none`, documented deviation) */
 } OracleCam;
 
 typedef struct {

@@ -72,7 +72,8 @@ def circle_mask(size=(224, 224), border=0):
 class SensorModel:
     """Static scene of one allsight sensor (renderer.py:137-163,291-325; wrapper :100-174)."""
 
-    def __init__(self, yml=SENSOR_YML, assets=ASSETS):
+    def __init__(self, yml=SENSOR_YML, assets=ASSETS, falloff=None):
+        """`falloff` overrides the yaml's `lights.falloff` (inverse_square | none; DESIGN.md "light model")."""
         conf = yaml.safe_load(open(yml))["sensor"]
         self.conf = conf
         cam = conf["camera"][0]
@@ -127,7 +128,9 @@ class SensorModel:
         m = conf["material"]
         c.base = (ctypes.c_float * 3)(*m["base_color"])
         c.metallic, c.roughness = m["metallic"], m["roughness"]
-        c.inverse_square = 1 if lg.get("falloff", "none") == "inverse_square" else 0
+        self.falloff = falloff if falloff is not None else lg.get("falloff", "inverse_square")
+        assert self.falloff in ("inverse_square", "none"), self.falloff
+        c.inverse_square = 1 if self.falloff == "inverse_square" else 0
         self._cam = c
         self.mask = circle_mask((W, H))
         # get_background_sim, renderer.py:165-168

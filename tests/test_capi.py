@@ -21,7 +21,7 @@ def test_version_and_error_string(built_lib):
 def test_bad_args_return_error_without_gpu(built_lib):
     lib = _lib.load()
     rc = lib.igi_fps(None, ctypes.c_int64(0), None, None, ctypes.c_int64(1), 0, 1, 4, None,
-                     ctypes.c_int64(12), None, None)
+                     ctypes.c_int64(12), None, 0, None)
     assert rc == -1
     assert b"igi_fps" in lib.igi_last_error()
 

@@ -91,6 +91,19 @@ def test_get_ptd_cuda_and_convert(golden, cam):
                                atol=_tol(gym))
 
 
+def test_proc_pts_uses_the_envs_own_camera(golden, cam):
+    """`_proc_pts(env_id, depth_image)` (pcl_utils.py:186-193) takes ONE image and that env's tables; any
+    env_id > 0 must work and equal the env's entry of the batched `get_ptd_cuda`."""
+    gym, gen = cam
+    depth = torch.from_numpy(golden["depth"]).cuda()
+    lst = gen.get_ptd_cuda(depth)
+    for e in (0, 1, depth.shape[0] - 1):
+        one = gen._proc_pts(e, depth[e])
+        assert torch.equal(one, lst[e]) and one.shape[0] > 0
+    sub = gen.get_ptd_cuda(depth, env_ids=[2, 0])
+    assert torch.equal(sub[0], lst[2]) and torch.equal(sub[1], lst[0])
+
+
 @pytest.mark.parametrize("n_envs,seed", [(1, 0), (67, 1), (300, 2)])
 def test_seeded_scenes_vs_oracle(built_lib, n_envs, seed):
     from isaacgyminsertion_b200.pcl_utils import CameraPointCloud, filter_pts
@@ -155,7 +168,7 @@ def test_fps_balanced_mixed_sizes(built_lib):
     scratch = torch.empty(T + 8, dtype=torch.int32, device="cuda")
     rc = lib.igi_fps_balanced(_lib.dptr(d_pts), c.c_int64(cap * 3), _lib.dptr(d_cnt), _lib.dptr(d_any), c.c_int64(1),
                               c.c_int(T), c.c_int(m), _lib.dptr(out), c.c_int64(m * 3), _lib.dptr(idx),
-                              _lib.dptr(scratch), _lib.stream_ptr(d_pts.device))
+                              _lib.dptr(scratch), c.c_int(0), _lib.stream_ptr(d_pts.device))
     _lib.check(rc, "igi_fps_balanced")
     sched = scratch[:5].cpu().numpy()
     live = (counts > 0) & (anyf != 0)
@@ -203,11 +216,7 @@ def test_fps_cluster_equals_block_kernel(built_lib):
         pts[4, 100:200] = pts[4, 0:100]
         d = torch.from_numpy(pts).cuda()
         a = furthest_point_sample(d, m).cpu().numpy()
-        try:
-            _lib.check(lib.igi_fps_set_cluster(0), "igi_fps_set_cluster")
-            b = furthest_point_sample(d, m).cpu().numpy()
-        finally:
-            lib.igi_fps_set_cluster(1)
+        b = furthest_point_sample(d, m, flags=1).cpu().numpy()      # IGI_FPS_NO_CLUSTER
         assert np.array_equal(a, b), (n, m)
         assert np.array_equal(a[4], ofps.furthest_point_sample(pts[4], m))
 
@@ -230,7 +239,7 @@ def test_fps_balanced_long_list_of_big_tasks(built_lib):
         scratch = torch.empty(T + 8, dtype=torch.int32, device="cuda")
         rc = lib.igi_fps_balanced(_lib.dptr(d_pts), c.c_int64(cap * 3), _lib.dptr(d_cnt), _lib.dptr(d_any), c.c_int64(1),
                                   c.c_int(T), c.c_int(m), None, c.c_int64(m * 3), _lib.dptr(idx), _lib.dptr(scratch),
-                                  _lib.stream_ptr(d_pts.device))
+                                  c.c_int(0), _lib.stream_ptr(d_pts.device))
         _lib.check(rc, "igi_fps_balanced")
         assert int(scratch[4]) == int((counts > 1024).sum())
         got = idx.cpu().numpy()

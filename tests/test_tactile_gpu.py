@@ -14,17 +14,19 @@ pytestmark = pytest.mark.gpu
 N_ENVS = 14
 
 
-@pytest.fixture(scope="module")
-def oracle_model():
+@pytest.fixture(scope="module", params=["inverse_square", "none"])
+def oracle_model(request):
+    """Every test below runs under both light models (DESIGN.md "light model"): the shipped default
+    `inverse_square` and the documented deviation `none` (unsaturated images)."""
     from oracle import tactile as ot
-    return ot.SensorModel()
+    return ot.SensorModel(falloff=request.param)
 
 
 @pytest.fixture(scope="module")
 def scene(oracle_model, built_lib):
     from isaacgyminsertion_b200.allsight_render import BatchedAllSight
     P = synthetic.tactile_poses(N_ENVS, oracle_model.assets, seed=0)
-    eng = BatchedAllSight(N_ENVS, P["mesh_id"], P["bg_id"], device="cuda:0")
+    eng = BatchedAllSight(N_ENVS, P["mesh_id"], P["bg_id"], device="cuda:0", falloff=oracle_model.falloff)
     return P, eng
 
 
@@ -88,15 +90,17 @@ def test_batched_render_matches_oracle(oracle_model, scene):
 def test_update_mask_keeps_previous_frame(scene):
     P, eng = scene
     _render(eng, P)
-    before = eng.obs.clone()
+    before, before_gd = eng.obs.clone(), eng.gel_depth.clone()
     P2 = {k: v.copy() for k, v in P.items()}
     P2["finger_pos"] = P2["finger_pos"] + np.float32(0.002)
     upd = torch.zeros(N_ENVS, dtype=torch.bool, device=eng.device)
     upd[::2] = True
     _render(eng, P2, update=upd)
     after = eng.obs
-    assert torch.equal(after[1::2], before[1::2])
-    assert not torch.equal(after[::2], before[::2])
+    assert torch.equal(after[1::2], before[1::2]) and torch.equal(eng.gel_depth[1::2], before_gd[1::2])
+    assert not torch.equal(eng.gel_depth[::2], before_gd[::2])
+    if eng.cfg.falloff == "none":          # under inverse_square the image never leaves the background
+        assert not torch.equal(after[::2], before[::2])
     assert (eng.contact_counts()[1::2] == -1).all()
 
 
@@ -136,18 +140,24 @@ def test_reference_style_handles(oracle_model, scene):
         assert tac.shape == (224, 224, 3)
 
 
-def test_coloured_lights_use_three_channel_path(built_lib, tmp_path):
-    """RGB lights (TACTO's default DIGIT look) take the 3-channel kernel instantiation."""
+@pytest.mark.parametrize("falloff,intensity", [("none", 0.5), ("inverse_square", 5e-4), ("inverse_square", 0.03)])
+def test_coloured_lights_use_three_channel_path(built_lib, tmp_path, falloff, intensity):
+    """RGB lights (TACTO's default DIGIT look) take the 3-channel kernel instantiation.  The dim inverse-square
+    case (5e-4 cd) keeps the 1/d^2 branch below the clip so its arithmetic is compared within 1/255; 0.03 cd is the
+    value of the reference's config_allsight_rgbrgbrgb.yml (partly saturated)."""
     import yaml
     from isaacgyminsertion_b200 import assets
     from isaacgyminsertion_b200.allsight_render import BatchedAllSight
     from oracle import tactile as ot
     conf = yaml.safe_load(open(assets.SENSOR_YML))
     conf["sensor"]["lights"]["colors"] = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    conf["sensor"]["lights"]["falloff"] = falloff
+    conf["sensor"]["lights"]["intensities"] = [intensity] * 3
     yml = tmp_path / "rgb.yml"
     yml.write_text(yaml.safe_dump(conf))
     model = ot.SensorModel(yml=str(yml))
-    assert len(np.unique(model.bg_sim.reshape(-1, 3), axis=0)) > 50
+    if intensity != 0.03:
+        assert len(np.unique(model.bg_sim.reshape(-1, 3), axis=0)) > 50 and model.bg_sim.max() < 255
     P = synthetic.tactile_poses(4, model.assets, seed=5)
     eng = BatchedAllSight(4, P["mesh_id"], P["bg_id"], device="cuda:0", sensor_yml=str(yml))
     _render(eng, P)
@@ -158,21 +168,57 @@ def test_coloured_lights_use_three_channel_path(built_lib, tmp_path):
         assert np.abs(eng.obs[e, n].cpu().numpy() - w["obs"]).max() <= 1.0 / 255 + 1e-6
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("IGI_TEST_EXPERIMENTAL"),
-                    reason="experimental gel_depth prefill (DESIGN.md section 8 item 0): not measured yet, set IGI_TEST_EXPERIMENTAL=1")
-def test_prefilled_gel_depth_equals_default_path(oracle_model, built_lib):
-    """gel_depth double-buffered and zeroed one step ahead by cudaMemsetAsync == the default path, over several
-    steps with changing poses and with an update mask that keeps some envs' previous frames."""
+def test_two_engines_with_different_sensors_share_a_process(built_lib, tmp_path):
+    """The library keeps no sensor state (constants travel with every call): two engines with different yamls,
+    rendered alternately, give what each gives alone."""
+    import yaml
+    from isaacgyminsertion_b200 import assets
     from isaacgyminsertion_b200.allsight_render import BatchedAllSight
-    n = 9
-    Ps = [synthetic.tactile_poses(n, oracle_model.assets, seed=s) for s in (0, 1, 2, 3)]
-    for P in Ps[1:]:
-        P["mesh_id"], P["bg_id"] = Ps[0]["mesh_id"], Ps[0]["bg_id"]        # static per engine
-    ref = BatchedAllSight(n, Ps[0]["mesh_id"], Ps[0]["bg_id"], device="cuda:0")
-    exp = BatchedAllSight(n, Ps[0]["mesh_id"], Ps[0]["bg_id"], device="cuda:0", prefill_gel_depth=True)
-    masks = [None, None, torch.tensor([1, 0, 1, 1, 0, 1, 1, 1, 0], dtype=torch.bool, device="cuda:0"), None]
-    for P, m in zip(Ps, masks):
-        _render(ref, P, update=m)
-        _render(exp, P, update=m)
-        assert torch.equal(ref.gel_depth, exp.gel_depth)
-        assert torch.equal(ref.color, exp.color) and torch.equal(ref.obs, exp.obs)
+    packed = assets.load_packed()
+    P = synthetic.tactile_poses(5, packed, seed=3)
+    conf = yaml.safe_load(open(assets.SENSOR_YML))
+    conf["sensor"]["lights"]["colors"] = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    conf["sensor"]["lights"]["falloff"] = "none"
+    conf["sensor"]["bg_calibration"]["scale_factor"] = 1.0
+    yml = tmp_path / "rgb.yml"
+    yml.write_text(yaml.safe_dump(conf))
+    alone = []
+    for kw in (dict(falloff="none"), dict(sensor_yml=str(yml))):
+        e = BatchedAllSight(5, P["mesh_id"], P["bg_id"], device="cuda:0", **kw)
+        _render(e, P)
+        alone.append((e.color.clone(), e.gel_depth.clone(), e.obs.clone(), e.bg_sim.clone()))
+    a = BatchedAllSight(5, P["mesh_id"], P["bg_id"], device="cuda:0", falloff="none")
+    b = BatchedAllSight(5, P["mesh_id"], P["bg_id"], device="cuda:0", sensor_yml=str(yml))
+    for _ in range(2):
+        _render(a, P)
+        _render(b, P)
+    for eng, ref in ((a, alone[0]), (b, alone[1])):
+        assert torch.equal(eng.color, ref[0]) and torch.equal(eng.gel_depth, ref[1])
+        assert torch.equal(eng.obs, ref[2]) and torch.equal(eng.bg_sim, ref[3])
+    assert not torch.equal(a.color, b.color) and not torch.equal(a.bg_sim, b.bg_sim)
+
+
+def test_triangle_list_overflow_is_surfaced_and_grown(oracle_model, built_lib):
+    """kmax too small: the device flag reaches the host without a sync; on_overflow='raise' raises at the next
+    poll, 'grow' re-allocates from the measured high-water mark, renders the step again and then matches a
+    roomy engine bit for bit."""
+    from isaacgyminsertion_b200.allsight_render import BatchedAllSight
+    P = synthetic.tactile_poses(N_ENVS, oracle_model.assets, seed=0)
+    roomy = BatchedAllSight(N_ENVS, P["mesh_id"], P["bg_id"], device="cuda:0", falloff=oracle_model.falloff)
+    _render(roomy, P)
+    assert roomy.check_overflow() is False
+    peak = int(roomy.contact_counts().max())
+    assert roomy.high_water == peak and peak > 64
+    strict = BatchedAllSight(N_ENVS, P["mesh_id"], P["bg_id"], device="cuda:0", kmax=32, on_overflow="raise",
+                             falloff=oracle_model.falloff)
+    _render(strict, P)
+    with pytest.raises(RuntimeError, match="overflow"):
+        strict.check_overflow()
+    grow = BatchedAllSight(N_ENVS, P["mesh_id"], P["bg_id"], device="cuda:0", kmax=32, falloff=oracle_model.falloff)
+    _render(grow, P)
+    torch.cuda.synchronize()
+    with pytest.warns(UserWarning, match="overflowed"):
+        _render(grow, P)                    # the poll at the start of this call sees the flag of the first one
+    assert grow.kmax >= peak and grow.check_overflow() is False
+    assert torch.equal(grow.gel_depth, roomy.gel_depth) and torch.equal(grow.color, roomy.color)
+    assert torch.equal(grow.obs, roomy.obs)

@@ -42,12 +42,13 @@ def _task(n, gym, P, **kw):
 
 
 # --------------------------------------------------------------------------------------------
-def test_cuda_matches_golden_fixture(built_lib, golden_dir):
-    """CUDA path against tests/golden/tactile_golden.npz; needs no oracle at run time."""
+@pytest.mark.parametrize("name", ["tactile_golden.npz", "tactile_golden_none.npz"])
+def test_cuda_matches_golden_fixture(built_lib, golden_dir, name):
+    """CUDA path against tests/golden/tactile_golden{,_none}.npz (one per light model); needs no oracle at run time."""
     from isaacgyminsertion_b200.allsight_render import BatchedAllSight
-    g = np.load(os.path.join(golden_dir, "tactile_golden.npz"))
+    g = np.load(os.path.join(golden_dir, name))
     n = int(g["n_envs"])
-    eng = BatchedAllSight(n, g["mesh_id"], g["bg_id"], device=DEV)
+    eng = BatchedAllSight(n, g["mesh_id"], g["bg_id"], device=DEV, falloff=str(g["falloff"]))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
     eng.render(t(g["finger_pos"]), t(g["finger_quat"]), t(g["plug_pos"]), t(g["plug_quat"]), force=float(g["force"]))
     eng.check_overflow()
@@ -97,6 +98,38 @@ def test_task_observation_functions_match_oracle(built_lib):
     assert float(task.tactile_queue[1].abs().max()) == 0 and int(task.got_socket[4]) == 0 and int(task.got_socket[0]) == 1
 
 
+def test_reset_then_masked_step_shows_zeros(built_lib):
+    """factory_task_insertion.py:1753-1777 zeroes queues AND current buffers of the reset envs; an env whose
+    update flags are off on the next step copies `tactile_queue[e, 0]` (= 0) (:578-579), keeps its zeroed pcl row
+    (:1014-1027 writes only `update` rows) and its zeroed seg_buf (:934-940)."""
+    n = 6
+    gym, P, depth, seg = _inputs(n, seed=3)
+    task = _task(n, gym, P, sampler="fps", falloff="none")
+    _load(task, P, depth, seg)
+    ones = torch.ones(n, dtype=torch.bool, device=DEV)
+    zeros = torch.zeros(n, dtype=torch.bool, device=DEV)
+    task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
+    assert float(task.tactile_imgs.abs().sum(-1).min()) > 0 and float(task.pcl.abs().sum(1).min()) > 0
+    assert int(task.seg_buf.abs().sum(1).min()) > 0
+    before = task.obs_packed.clone()
+    ids = torch.tensor([1, 4], device=DEV)
+    task.reset_idx(ids)
+    for buf in (task.tactile_imgs, task.tactile_queue, task.pcl, task.pcl_queue, task.socket_pcl, task.seg_buf,
+                task.got_socket):
+        assert float(buf[ids].abs().sum()) == 0, "reset must zero the current buffers, not only the queues"
+    upd = ones.clone()
+    upd[ids] = False                     # the reset envs are not updated on the next step
+    task.compute_observations(upd, ones, upd, ones, ones, zeros, zeros)
+    assert float(task.tactile_imgs[ids].abs().sum()) == 0 and float(task.tactile_queue[ids].abs().sum()) == 0
+    assert int(task.seg_buf[ids].abs().sum()) == 0
+    # pcl: got_socket was cleared, so the socket cloud is recomputed and the row rewritten (`update | restarted`, :988-989)
+    assert float(task.pcl[ids].abs().sum()) > 0 and int(task.got_socket.min()) == 1
+    keep = torch.tensor([0, 2, 3, 5], device=DEV)
+    assert torch.equal(task.obs_packed[keep], before[keep])
+    task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
+    assert torch.equal(task.obs_packed, before)
+
+
 def test_include_all_pcl_matches_oracle(built_lib):
     """include_all_pcl (FactoryTaskInsertionTactile.yaml:124): the unmasked scene cloud is drawn FIRST from the
     torch.randint stream (factory_task_insertion.py:946-949) and appended LAST to the pcl row (:1014-1027)."""
@@ -137,22 +170,18 @@ def test_multi_region_path_is_identical(built_lib):
     n = 7
     packed = assets.load_packed()
     P = synthetic.tactile_poses(n, packed, seed=2)
-    eng = BatchedAllSight(n, P["mesh_id"], P["bg_id"], device=DEV)
+    eng = BatchedAllSight(n, P["mesh_id"], P["bg_id"], device=DEV, falloff="none")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
     args = (t(P["finger_pos"]), t(P["finger_quat"]), t(P["plug_pos"]), t(P["plug_quat"]))
-    lib = _lib.load()
     eng.render(*args)
     ref = (eng.color.clone(), eng.gel_depth.clone(), eng.obs.clone())
     assert int((eng.contact_counts() > 0).sum()) >= 5
-    try:
-        for budget in (49 + 15, 700, 3000):
-            _lib.check(lib.igi_tactile_set_region_budget(budget), "igi_tactile_set_region_budget")
-            eng.color.zero_(); eng.gel_depth.fill_(-1); eng.obs.zero_()
-            eng.render(*args)
-            assert torch.equal(eng.color, ref[0]) and torch.equal(eng.gel_depth, ref[1]), budget
-            assert torch.equal(eng.obs, ref[2]), budget
-    finally:
-        lib.igi_tactile_set_region_budget(0)
+    for budget in (49 + 15, 700, 3000):
+        eng.region_budget = budget          # IgiTactileFrames.region_budget (test hook, per call)
+        eng.color.zero_(); eng.gel_depth.fill_(-1); eng.obs.zero_()
+        eng.render(*args)
+        assert torch.equal(eng.color, ref[0]) and torch.equal(eng.gel_depth, ref[1]), budget
+        assert torch.equal(eng.obs, ref[2]), budget
 
 
 def test_host_pipeline_matches_direct_calls(built_lib):
@@ -171,7 +200,8 @@ def test_host_pipeline_matches_direct_calls(built_lib):
     # second set of poses so that consecutive steps differ
     P2 = dict(P)
     P2["finger_pos"] = P["finger_pos"] + np.float32(0.0015)
-    host2 = [pin(P2[k]) for k in ("finger_pos", "finger_quat", "plug_pos", "plug_quat")] + [pin(depth), pin(seg)]
+    # (under the default light model the tactile image never leaves the background, so the cloud must differ too)
+    host2 = [pin(P2[k]) for k in ("finger_pos", "finger_quat", "plug_pos", "plug_quat")] + [pin(depth * np.float32(1.01)), pin(seg)]
     pipe = HostObsPipeline(task, sampler_socket_every_step=True)
     pending = [pipe.step(*(host if i % 2 == 0 else host2)) for i in range(5)]
     outs = [p.wait().clone() for p in pending[-3:]]      # ring of 3 slots: the last three are still valid
@@ -181,10 +211,10 @@ def test_host_pipeline_matches_direct_calls(built_lib):
 
 
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_envs", [1024, 4096])
-def test_full_size_tactile_properties(built_lib, n_envs):
+@pytest.mark.parametrize("n_envs,falloff", [(1024, "inverse_square"), (4096, "inverse_square"), (4096, "none")])
+def test_full_size_tactile_properties(built_lib, n_envs, falloff):
     gym, P, depth, seg = _inputs(n_envs, seed=0)
-    task = _task(n_envs, gym, P, sampler="fps", pcl_cam=False)
+    task = _task(n_envs, gym, P, sampler="fps", pcl_cam=False, falloff=falloff)
     _load(task, P, depth, seg)
     eng = task.tactile_engine
     ones = torch.ones(n_envs, dtype=torch.bool, device=DEV)
@@ -215,6 +245,7 @@ def test_full_size_tactile_properties(built_lib, n_envs):
     assert torch.equal(obs2, obs)
     # determinism and the update mask
     snap = (obs.clone(), color[::97].clone())
+    gd_snap = gd.reshape(n_envs, 3, 224, 224)[::16].clone()
     task.update_tactile(ones, ones)
     assert torch.equal(task.tactile_imgs.reshape(F, 2048), snap[0]) and torch.equal(color[::97], snap[1])
     task.plug_pos = task.plug_pos + 0.001
@@ -223,7 +254,11 @@ def test_full_size_tactile_properties(built_lib, n_envs):
     task.update_tactile(half, ones)
     now = task.tactile_imgs.reshape(n_envs, 3, 2048)
     assert torch.equal(now[n_envs // 2:], snap[0].reshape(n_envs, 3, 2048)[n_envs // 2:])
-    assert not torch.equal(now[: n_envs // 2], snap[0].reshape(n_envs, 3, 2048)[: n_envs // 2])
+    gd_now = eng.gel_depth.reshape(n_envs, 3, 224, 224)[::16]
+    k = gd_now.shape[0] // 2
+    assert torch.equal(gd_now[k:], gd_snap[k:]) and not torch.equal(gd_now[:k], gd_snap[:k])
+    if falloff == "none":      # under inverse_square every fragment clips like the gel behind it: the image stays the background
+        assert not torch.equal(now[: n_envs // 2], snap[0].reshape(n_envs, 3, 2048)[: n_envs // 2])
 
 
 @pytest.mark.parametrize("n_envs", [1024, 4096])
@@ -307,9 +342,9 @@ def test_edge_cases(built_lib):
     import ctypes as c
     buf = torch.zeros((n, 400, 3), device=DEV)
     rc = lib.igi_fps(_lib.dptr(buf), c.c_int64(1200), None, None, c.c_int64(1), c.c_int(400), c.c_int(0),
-                     c.c_int(16), _lib.dptr(buf), c.c_int64(1200), None, _lib.stream_ptr(task.device))
+                     c.c_int(16), _lib.dptr(buf), c.c_int64(1200), None, c.c_int(0), _lib.stream_ptr(task.device))
     assert rc == 0 and lib.igi_launch_count() == before
     rc = lib.igi_fps_balanced(_lib.dptr(buf), c.c_int64(1200), _lib.dptr(task.got_socket), None, c.c_int64(1), c.c_int(0),
                               c.c_int(16), _lib.dptr(buf), c.c_int64(1200), None, _lib.dptr(task.got_socket),
-                              _lib.stream_ptr(task.device))
+                              c.c_int(0), _lib.stream_ptr(task.device))
     assert rc == 0 and lib.igi_launch_count() == before

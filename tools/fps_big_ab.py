@@ -11,14 +11,13 @@ for B, n, m in ((8, 5184, 2048), (64, 5184, 2048), (512, 5184, 400), (4096, 2048
     pts = torch.rand((B, n, 3), device="cuda", generator=g) * 0.5 + 0.1
     res = {}
     for mode in (1, 0):
-        lib.igi_fps_set_cluster(mode)
+        fl = 0 if mode else 1      # IGI_FPS_NO_CLUSTER
         for _ in range(2):
-            idx = furthest_point_sample(pts, m)
+            idx = furthest_point_sample(pts, m, flags=fl)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for _ in range(3):
-            idx = furthest_point_sample(pts, m)
+            idx = furthest_point_sample(pts, m, flags=fl)
         e1.record(); torch.cuda.synchronize()
         res[mode] = (e0.elapsed_time(e1) / 3, idx)
-    lib.igi_fps_set_cluster(1)
     print(f"tasks {B:5d} x {n} points, m={m}: cluster {res[1][0]:8.3f} ms   one-CTA {res[0][0]:8.3f} ms   equal {bool(torch.equal(res[1][1], res[0][1]))}")

@@ -7,7 +7,12 @@ is this repo's statement of pyrender's behaviour (parity unpinned).  The fixture
 either (a cv2 upgrade changing INTER_AREA, an edit of raster.c) and give the CUDA path a fixed
 target that does not need the oracle at test time.
 
-    python tools/make_golden_tactile.py     ->  tests/golden/tactile_golden.npz
+Two files, one per light model (DESIGN.md "light model"): tactile_golden.npz is the shipped default
+(`falloff: inverse_square`: every fragment saturates, the colour image equals the background and only
+gel_depth carries the contact), tactile_golden_none.npz the documented deviation (`falloff: none`), whose
+unsaturated images exercise the shading + calibration arithmetic.
+
+    python tools/make_golden_tactile.py     ->  tests/golden/tactile_golden{,_none}.npz
 """
 import os
 import sys
@@ -24,7 +29,12 @@ N_ENVS = 14   # two envs per peg: 42 frames with the 50/25/25 contact mix
 
 
 def main():
-    model = ot.SensorModel()
+    for falloff, name in (("inverse_square", "tactile_golden.npz"), ("none", "tactile_golden_none.npz")):
+        make(falloff, name)
+
+
+def make(falloff, name):
+    model = ot.SensorModel(falloff=falloff)
     P = synthetic.tactile_poses(N_ENVS, model.assets, seed=0)
     obj_tf = ot.xyzquat_to_tf_numpy(np.concatenate([P["plug_pos"], P["plug_quat"]], 1))
     M, gd, delta, obs = [], [], [], []
@@ -38,9 +48,9 @@ def main():
             gd.append(gel_depth)
             delta.append(color.astype(np.int16) - h.bg_img.astype(np.int16))   # sparse: compresses well
             obs.append(ot.tactile_obs(color, h.bg_img, h.mask))
-    out = os.path.join(ROOT, "tests", "golden", "tactile_golden.npz")
+    out = os.path.join(ROOT, "tests", "golden", name)
     np.savez_compressed(
-        out, n_envs=N_ENVS, seed=0, force=70.0,
+        out, n_envs=N_ENVS, seed=0, force=70.0, falloff=falloff,
         finger_pos=P["finger_pos"], finger_quat=P["finger_quat"], plug_pos=P["plug_pos"], plug_quat=P["plug_quat"],
         mesh_id=P["mesh_id"], bg_id=P["bg_id"], M=np.stack(M).astype(np.float32), gel_depth=np.stack(gd),
         color_delta=np.stack(delta), obs=np.stack(obs).astype(np.float32),

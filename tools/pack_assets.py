@@ -15,7 +15,8 @@ What is packed (and which reference line consumes the original):
   peg_<i>_v / _f / _vn    the 7 default plug meshes
                           (FactoryEnvInsertionTactile.yaml:47-55,
                           factory_env_insertion.py:1037-1053): vertices merged on
-                          position (trimesh.load default), x,y * asset scale
+                          position AND file normal (trimesh.load -> merge_vertices
+                          defaults: merge_norm=False, 8 / 2 digits), x,y * asset scale
                           (allsight_render.py:101-107), angle-weighted vertex
                           normals recomputed after scaling (SURVEY T2 decision).
   bg_real    (8,224,224,3) u8  ref_frame_white{12..19}.jpg, cv2.resize to
@@ -64,8 +65,8 @@ def main():
         plug = info[sub][comps[0]]
         f = plug["urdf_path"]
         f += "_subdiv_3x.obj" if ("rectangular" in f or "square" in f) else ".obj"
-        V, F = load_obj(f"{REF}/assets/factory/mesh/factory_insertion/{f}")
-        V, F = merge_vertices(V, F)
+        V, F, VNfile = load_obj(f"{REF}/assets/factory/mesh/factory_insertion/{f}", with_normals=True)
+        V, F = merge_vertices(V, F, VNfile)
         s = float(plug["scale"])
         V[:, 0] *= s
         V[:, 1] *= s
