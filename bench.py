@@ -302,8 +302,7 @@ def main():
                 pending[0] = dist.all_gather_into_tensor(gathered[i & 1], buf, async_op=True)
 
     def obs_step(i):
-        task._socket_pending = True   # worst case: every env restarted -> socket cloud recomputed each step
-        task.got_socket.zero_()
+        task.invalidate_socket_cache()   # worst case: every env restarted -> socket cloud recomputed each step
         # update_tactile + update_external_cam with the reference's mask arguments (task :862-887)
         task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
         if world > 1:
@@ -376,8 +375,7 @@ def main():
         t_contact = timed(stage(4), K, 3) / K
 
         def pcl_only(i):
-            task._socket_pending = True
-            task.got_socket.zero_()
+            task.invalidate_socket_cache()
             task.update_external_cam(ones, ones, ones, zeros, zeros)
         t_pcl = timed(pcl_only, K, 3) / K
         gen = task.pcl_generator.engine

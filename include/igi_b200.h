@@ -168,13 +168,19 @@ typedef struct IgiTactileStatic {
  * (factory_task_insertion.py:481-484), frame f = env*sensors_per_env + sensor. */
 typedef struct IgiTactileFrames {
   int32_t n_envs, sensors_per_env;
-  const float* finger_pos;      /* (n_envs*S,3) */
-  const float* finger_quat;     /* (n_envs*S,4) xyzw */
+  const float* finger_pos;      /* (n_envs*S,3), or NULL: sensor n's positions at finger_pos_n[n] + env*finger_pos_stride */
+  const float* finger_quat;     /* (n_envs*S,4) xyzw, or NULL: finger_quat_n[n] + env*finger_quat_stride */
   const float* plug_pos;        /* (n_envs,3) */
   const float* plug_quat;       /* (n_envs,4) xyzw */
   const float* force;           /* (n_envs*S) normal force or NULL -> force_const (70, task :535) */
   float force_const;
   const uint8_t* update;        /* (n_envs) update_freq & update_delay or NULL (all) (task :523) */
+  const uint8_t* update2;       /* (n_envs) or NULL: second mask ANDed with `update`, so update_freq and update_delay can be
+                                   passed as they are (no logical_and launch) */
+  const float* finger_pos_n[8]; /* used when finger_pos == NULL: the reference's per-fingertip state views
+                                   (left/right/middle_finger_pos, factory_task_insertion.py:481-483) without a stack copy */
+  const float* finger_quat_n[8];
+  int64_t finger_pos_stride, finger_quat_stride; /* floats between consecutive envs of one sensor's view */
   const int32_t* mesh_id;       /* (n_envs) */
   const int32_t* bg_id;         /* (n_envs*S) index into bg_real */
   int32_t stage_mask;           /* 0 = whole pipeline (= 8|4).  bits: 1 geometry alone, 2 standalone fill,
@@ -318,11 +324,27 @@ int igi_traj_gather(void* buf, const int32_t* ids, const int32_t* n_ids, int max
 /* counter[ids[j]] = 0 for j < min(*n_ids, max_ids)   (_reset_buffers, experience.py:420). */
 int igi_traj_reset_counters(long long* counter, const int32_t* ids, const int32_t* n_ids, int max_ids, void* stream);
 
-/* dst[r, :] = src[r, :] for the rows r whose flag[r] != 0 equals want != 0; rows of row_bytes (multiple of 16) bytes.
- * Used to carry frames an update mask leaves untouched (factory_task_insertion.py:523,578-579) from one output buffer to
- * the other when outputs are double-buffered over steps. */
-int igi_copy_rows_where(void* dst, const void* src, const uint8_t* flag, int want, long long rows, long long row_bytes,
-                        void* stream);
+/* dst[r, :] = src[r, :] for the rows r whose flag[r] != 0 equals want != 0; rows of row_bytes (multiple of 16) bytes at
+ * dst + r*dst_stride_bytes / src + r*src_stride_bytes.
+ * Replaces: `self.seg_buf[update_seg] = seg[update_seg]` factory_task_insertion.py:934-940 (and any masked row write). */
+int igi_copy_rows_where(void* dst, long long dst_stride_bytes, const void* src, long long src_stride_bytes,
+                        const uint8_t* flag, int want, long long rows, long long row_bytes, void* stream);
+
+/* The per-env masks of one update_external_cam call in ONE launch (bool tensors are 1 byte per env):
+ *   upd_seg   = update_freq & seg_update_delay                                 factory_task_insertion.py:934-940 (NULL: skip)
+ *   restarted = socket_pending & (got_socket == 0); got_socket[restarted] = 1   :981,:987
+ *               (socket_pending == 2: every env counts as restarted, e.g. after a reset of all envs)
+ *   upd_pcl   = (update_freq & update_delay) | restarted                        :896-897,:988-989 */
+int igi_cam_masks(const uint8_t* update_freq, const uint8_t* update_delay, const uint8_t* seg_update_delay,
+                  int32_t* got_socket, int socket_pending, uint8_t* upd_seg, uint8_t* upd_pcl, uint8_t* restarted,
+                  int n_envs, void* stream);
+
+/* pcl[e, :] = src[e, :] where update[e] (NULL: every row), then the history push pcl_queue[:, 1:] = pcl_queue[:, :-1];
+ * pcl_queue[:, 0] = pcl, one pass.  Replaces factory_task_insertion.py:1027 and :1046-1048.
+ *   src row e at src + e*src_stride floats, pcl row e at pcl + e*pcl_stride floats (the pcl part of the packed
+ *   observation row); queue (n_envs, hist_len, row_len) f32 or NULL; row_len % 4 == 0, rows 16-byte aligned. */
+int igi_pcl_assemble(const float* src, int64_t src_stride, float* pcl, int64_t pcl_stride, const uint8_t* update,
+                     float* queue, int n_envs, int hist_len, long long row_len, void* stream);
 
 /* ----------------------------------------------------------------------------
  * (G) gather of the packed observation rows onto the learner rank without SM work.

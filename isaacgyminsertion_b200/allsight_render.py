@@ -64,7 +64,10 @@ class IgiTactileFrames(_c.Structure):
                 ("finger_pos", _c.c_void_p), ("finger_quat", _c.c_void_p),
                 ("plug_pos", _c.c_void_p), ("plug_quat", _c.c_void_p),
                 ("force", _c.c_void_p), ("force_const", _c.c_float),
-                ("update", _c.c_void_p), ("mesh_id", _c.c_void_p), ("bg_id", _c.c_void_p),
+                ("update", _c.c_void_p), ("update2", _c.c_void_p),
+                ("finger_pos_n", _c.c_void_p * 8), ("finger_quat_n", _c.c_void_p * 8),
+                ("finger_pos_stride", _c.c_int64), ("finger_quat_stride", _c.c_int64),
+                ("mesh_id", _c.c_void_p), ("bg_id", _c.c_void_p),
                 ("stage_mask", _c.c_int32), ("region_budget", _c.c_int32), ("fill_split", _c.c_int32)]
 
 
@@ -391,10 +394,12 @@ class BatchedAllSight:
     # ------------------------------------------------------------------------------------
     @torch.no_grad()
     def render(self, finger_pos, finger_quat, plug_pos, plug_quat, force=None, update=None, obs_out=None,
-               stage_mask=0, _poll=True):
-        """One batched pass.  finger_pos (N,S,3), finger_quat (N,S,4 xyzw), plug_pos (N,3),
-        plug_quat (N,4) f32 CUDA tensors; force: None (=70, factory_task_insertion.py:535),
-        scalar, or (N,S) tensor; update: None or (N,) bool/uint8 (task :523).
+               stage_mask=0, _poll=True, update2=None):
+        """One batched pass.  finger_pos (N,S,3), finger_quat (N,S,4 xyzw) f32 CUDA tensors - or a list of S
+        per-fingertip views (N,3) / (N,4) with unit inner stride and a common env stride, as the reference holds
+        them (left/right/middle_finger_pos, factory_task_insertion.py:481-483): no stack copy; plug_pos (N,3),
+        plug_quat (N,4); force: None (=70, factory_task_insertion.py:535), scalar, or (N,S) tensor; update /
+        update2: None or (N,) bool/uint8 masks, ANDed (update_freq & update_delay, task :523).
         Fills self.color / self.gel_depth / obs (default self.obs, shape (N,S,2048)); frames of
         envs whose update flag is off are left untouched."""
         if _poll and stage_mask == 0:
@@ -405,13 +410,34 @@ class BatchedAllSight:
             raise RuntimeError("obs_out must be a (N,S,2048) f32 CUDA tensor with unit inner stride")
         fr = IgiTactileFrames()
         fr.n_envs, fr.sensors_per_env = self.N, self.S
-        fp = finger_pos.reshape(self.F, 3)
-        fq = finger_quat.reshape(self.F, 4)
-        fr.finger_pos = _lib.dptr(fp, torch.float32, "finger_pos").value
-        fr.finger_quat = _lib.dptr(fq, torch.float32, "finger_quat").value
+        keep = []
+
+        def poses(x, width, name):
+            """-> (packed pointer or None, per-sensor pointers, env stride)"""
+            if isinstance(x, (list, tuple)):
+                views = list(x)
+                ok = len(views) == self.S and all(
+                    v.is_cuda and v.dtype == torch.float32 and v.shape == (self.N, width) and v.stride(1) == 1
+                    and v.stride(0) == views[0].stride(0) and v.stride(0) >= width for v in views)
+                if ok:
+                    keep.extend(views)
+                    return None, [v.data_ptr() for v in views], views[0].stride(0)
+                x = torch.stack([v.float() for v in views], dim=1)
+            t = x.reshape(self.F, width)
+            if not t.is_contiguous() or t.dtype != torch.float32:
+                t = t.contiguous().float()
+            keep.append(t)
+            return _lib.dptr(t, torch.float32, name).value, [], 0
+        p, pn, ps = poses(finger_pos, 3, "finger_pos")
+        q, qn, qs = poses(finger_quat, 4, "finger_quat")
+        fr.finger_pos, fr.finger_quat = p, q
+        for k, v in enumerate(pn):
+            fr.finger_pos_n[k] = v
+        for k, v in enumerate(qn):
+            fr.finger_quat_n[k] = v
+        fr.finger_pos_stride, fr.finger_quat_stride = ps, qs
         fr.plug_pos = _lib.dptr(plug_pos, torch.float32, "plug_pos").value
         fr.plug_quat = _lib.dptr(plug_quat, torch.float32, "plug_quat").value
-        keep = [fp, fq]
         fr.force_const = 70.0
         if force is None:
             fr.force = None
@@ -422,12 +448,14 @@ class BatchedAllSight:
         else:
             fr.force = None
             fr.force_const = float(force)
-        if update is not None:
-            up = update.to(torch.uint8).contiguous()
+        def mask(m, name):
+            if m is None:
+                return None
+            # a bool tensor is one byte (0 / 1) per env: passed as it is
+            up = m.view(torch.uint8) if m.dtype == torch.bool and m.is_contiguous() else m.to(torch.uint8).contiguous()
             keep.append(up)
-            fr.update = _lib.dptr(up, torch.uint8, "update").value
-        else:
-            fr.update = None
+            return _lib.dptr(up, torch.uint8, name).value
+        fr.update, fr.update2 = mask(update, "update"), mask(update2, "update2")
         fr.mesh_id, fr.bg_id = self.mesh_id.data_ptr(), self.bg_index.data_ptr()
         fr.stage_mask = int(stage_mask)
         fr.region_budget, fr.fill_split = int(self.region_budget), int(self.fill_split)
@@ -444,7 +472,7 @@ class BatchedAllSight:
             self._ovf_host.copy_(self._counters[2:4], non_blocking=True)
             self._ovf_event = torch.cuda.Event()
             self._ovf_event.record(torch.cuda.current_stream(self.device))
-            self._last_args = (finger_pos, finger_quat, plug_pos, plug_quat, force, update, obs_out)
+            self._last_args = (finger_pos, finger_quat, plug_pos, plug_quat, force, update, obs_out, update2)
         return obs
 
     # ------------------------------------------------------------------------------------
@@ -477,8 +505,8 @@ class BatchedAllSight:
         self._alloc_lists()
         self._structs()
         if self._last_args is not None:
-            fp, fq, pp, pq, force, update, obs_out = self._last_args
-            self.render(fp, fq, pp, pq, force=force, update=update, obs_out=obs_out, _poll=False)
+            fp, fq, pp, pq, force, update, obs_out, update2 = self._last_args
+            self.render(fp, fq, pp, pq, force=force, update=update, obs_out=obs_out, _poll=False, update2=update2)
         return True
 
     def check_overflow(self):

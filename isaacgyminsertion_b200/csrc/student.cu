@@ -283,15 +283,60 @@ __global__ void __launch_bounds__(256) queue_push_kernel(float* q, const TIn* __
 
 // dst[r, :] = src[r, :] for the rows whose flag equals `want` (rows of row16 uint4 each); rows that do not match cost
 // one flag read.  grid = (chunks, rows).
-__global__ void __launch_bounds__(256) copy_rows_where_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+__global__ void __launch_bounds__(256) copy_rows_where_kernel(uint4* __restrict__ dst, long long dst_stride16,
+                                                              const uint4* __restrict__ src, long long src_stride16,
                                                               const uint8_t* __restrict__ flag, int want, long long rows,
                                                               long long row16) {
   for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
     if ((flag[r] != 0) != (want != 0)) continue;
-    const uint4* s = src + (size_t)r * row16;
-    uint4* d = dst + (size_t)r * row16;
+    const uint4* s = src + (size_t)r * src_stride16;
+    uint4* d = dst + (size_t)r * dst_stride16;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row16; i += (long long)gridDim.x * blockDim.x)
       __stcs(d + i, __ldcs(s + i));
+  }
+}
+
+// Masks of one update_external_cam call (factory_task_insertion.py:896-989), one thread per env:
+//   upd_seg = update_freq & seg_update_delay                      (:934-940)
+//   restarted = socket_pending & (got_socket == 0)                (:981)
+//   upd_pcl = (update_freq & update_delay) | restarted            (:988-989); got_socket[restarted] = 1
+__global__ void __launch_bounds__(256) cam_masks_kernel(const uint8_t* __restrict__ freq, const uint8_t* __restrict__ delay,
+                                                        const uint8_t* __restrict__ seg_delay, int32_t* __restrict__ got_socket,
+                                                        int socket_pending, uint8_t* __restrict__ upd_seg,
+                                                        uint8_t* __restrict__ upd_pcl, uint8_t* __restrict__ restarted, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const bool f = freq[e] != 0;
+  const bool r = socket_pending == 2 || (socket_pending && got_socket[e] == 0);   // 2: every env counts as restarted
+  if (upd_seg) upd_seg[e] = (f && seg_delay[e] != 0) ? 1 : 0;
+  upd_pcl[e] = ((f && delay[e] != 0) || r) ? 1 : 0;
+  if (restarted) restarted[e] = r ? 1 : 0;
+  if (r) got_socket[e] = 1;
+}
+
+// pcl[e, :] = src[e, :] where update[e]  (factory_task_insertion.py:1027), then the history queue push
+// q[:, 1:] = q[:, :-1]; q[:, 0] = pcl  (:1046-1048), in one pass over the rows.
+__global__ void __launch_bounds__(256) pcl_assemble_kernel(const float4* __restrict__ src, int64_t src_stride4,
+                                                           float4* __restrict__ pcl, int64_t pcl_stride4,
+                                                           const uint8_t* __restrict__ update, float4* __restrict__ q, int n,
+                                                           int T, long long L4) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < (long long)n * L4;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(v / L4);
+    const long long j = v - (long long)e * L4;
+    float4* prow = pcl + (size_t)e * pcl_stride4 + j;
+    float4 val;
+    if (update == nullptr || update[e] != 0) {
+      val = __ldg(src + (size_t)e * src_stride4 + j);
+      *prow = val;
+    } else {
+      val = *prow;
+    }
+    if (q) {
+      float4* row = q + (size_t)e * T * L4 + j;
+      for (int t = T - 1; t > 0; --t) row[(size_t)t * L4] = row[(size_t)(t - 1) * L4];
+      row[0] = val;
+    }
   }
 }
 
@@ -398,10 +443,12 @@ extern "C" int igi_queue_push(float* queue, const void* x, int x_is_int32, int64
   return IGI_OK;
 }
 
-extern "C" int igi_copy_rows_where(void* dst, const void* src, const uint8_t* flag, int want, long long rows,
-                                   long long row_bytes, void* stream) {
+extern "C" int igi_copy_rows_where(void* dst, long long dst_stride_bytes, const void* src, long long src_stride_bytes,
+                                   const uint8_t* flag, int want, long long rows, long long row_bytes, void* stream) {
   IGI_REQUIRE(dst && src && flag, "igi_copy_rows_where: null pointer");
   IGI_REQUIRE(rows >= 0 && row_bytes > 0 && row_bytes % 16 == 0, "igi_copy_rows_where: row_bytes must be a positive multiple of 16");
+  IGI_REQUIRE(dst_stride_bytes >= row_bytes && src_stride_bytes >= row_bytes && dst_stride_bytes % 16 == 0 &&
+                  src_stride_bytes % 16 == 0, "igi_copy_rows_where: strides must be multiples of 16 and >= row_bytes");
   IGI_REQUIRE(((uintptr_t)dst % 16) == 0 && ((uintptr_t)src % 16) == 0, "igi_copy_rows_where: buffers must be 16-byte aligned");
   if (rows == 0) return IGI_OK;
   const long long row16 = row_bytes / 16;
@@ -409,7 +456,38 @@ extern "C" int igi_copy_rows_where(void* dst, const void* src, const uint8_t* fl
   if (gx > 32) gx = 32;
   const long long gy = rows < 65535 ? rows : 65535;
   copy_rows_where_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream>>>(
-      (uint4*)dst, (const uint4*)src, flag, want, rows, row16);
+      (uint4*)dst, dst_stride_bytes / 16, (const uint4*)src, src_stride_bytes / 16, flag, want, rows, row16);
   IGI_CHECK_LAUNCH("copy_rows_where_kernel");
+  return IGI_OK;
+}
+
+extern "C" int igi_cam_masks(const uint8_t* update_freq, const uint8_t* update_delay, const uint8_t* seg_update_delay,
+                             int32_t* got_socket, int socket_pending, uint8_t* upd_seg, uint8_t* upd_pcl,
+                             uint8_t* restarted, int n_envs, void* stream) {
+  IGI_REQUIRE(update_freq && update_delay && upd_pcl && n_envs >= 0, "igi_cam_masks: null pointer");
+  IGI_REQUIRE(!upd_seg || seg_update_delay, "igi_cam_masks: upd_seg needs seg_update_delay");
+  IGI_REQUIRE(!socket_pending || got_socket, "igi_cam_masks: socket_pending needs got_socket");
+  if (n_envs == 0) return IGI_OK;
+  cam_masks_kernel<<<(n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(update_freq, update_delay, seg_update_delay,
+                                                                           got_socket, socket_pending, upd_seg, upd_pcl,
+                                                                           restarted, n_envs);
+  IGI_CHECK_LAUNCH("cam_masks_kernel");
+  return IGI_OK;
+}
+
+extern "C" int igi_pcl_assemble(const float* src, int64_t src_stride, float* pcl, int64_t pcl_stride, const uint8_t* update,
+                                float* queue, int n_envs, int hist_len, long long row_len, void* stream) {
+  IGI_REQUIRE(src && pcl, "igi_pcl_assemble: null pointer");
+  IGI_REQUIRE(n_envs >= 0 && hist_len >= 1 && row_len > 0 && row_len % 4 == 0 && src_stride >= row_len &&
+                  pcl_stride >= row_len && src_stride % 4 == 0 && pcl_stride % 4 == 0,
+              "igi_pcl_assemble: row_len and strides must be multiples of 4, strides >= row_len");
+  IGI_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)pcl % 16) == 0 && ((uintptr_t)queue % 16) == 0,
+              "igi_pcl_assemble: buffers must be 16-byte aligned");
+  if (n_envs == 0) return IGI_OK;
+  const long long items = (long long)n_envs * (row_len / 4);
+  pcl_assemble_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(src), src_stride / 4, reinterpret_cast<float4*>(pcl), pcl_stride / 4, update,
+      reinterpret_cast<float4*>(queue), n_envs, hist_len, row_len / 4);
+  IGI_CHECK_LAUNCH("pcl_assemble_kernel");
   return IGI_OK;
 }

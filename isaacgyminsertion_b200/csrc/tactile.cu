@@ -216,7 +216,11 @@ __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ft
 // the oracle within 1/255.
 // NL = number of lights when known at compile time (the loop unrolls and the light constants become
 // immediate constant-bank operands), 0 = kc.n_lights.
-template <int NCH, int NL>
+// EARLY (callers whose 32 lanes are converged): the light loop stops once every lane's sum has reached 1.0 in every
+// channel.  Each light adds a non-negative term (n.l >= 0.001, attenuation >= 0, BRDF terms >= 0) and the output
+// clamps at 1.0 -> 255, so the result is bit-identical; it only skips work for fragments that clip (every
+// fragment under the inverse-square light model with the shipped intensities).
+template <int NCH, int NL, bool EARLY = false>
 __device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t* rgb) {
   const float A2_PI = kc.sh_a2 * 0.31830988618379067f;
   const float ipl = fast_rsqrt(p.x * p.x + p.y * p.y + p.z * p.z);
@@ -256,6 +260,12 @@ __device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t*
     for (int k = 0; k < NCH; ++k) {
       const float F = kc.sh_f0[k] + (kc.sh_f90 - kc.sh_f0[k]) * fw;
       col[k] += na * kc.sh_rad[i][k] * ((1.0f - F) * kc.sh_cdiff_pi[k] + F * sp);
+    }
+    if (EARLY) {
+      bool clipped = true;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) clipped = clipped && col[k] >= 1.0f;
+      if (__all_sync(0xffffffffu, clipped)) break;
     }
   }
 #pragma unroll
@@ -367,12 +377,14 @@ struct MeshInfo { int face_off, n_faces, cl_off, n_cl; };
 struct Cluster { float cx, cy, cz, r; int first, count, pad0, pad1; };
 
 struct GeomArgs {
-  const float* finger_pos;   // (F,3)   frame f = env*S + sensor
-  const float* finger_quat;  // (F,4) xyzw
+  const float* fpos_n[8];    // sensor n's positions at fpos_n[n] + env*fpos_stride (frame f = env*S + sensor)
+  const float* fquat_n[8];   // sensor n's quaternions (xyzw) at fquat_n[n] + env*fquat_stride
+  int64_t fpos_stride, fquat_stride;
   const float* plug_pos;     // (N,3)
   const float* plug_quat;    // (N,4)
   const float* force;        // (F) or null -> force_const
   const uint8_t* update;     // (N) or null
+  const uint8_t* update2;    // (N) or null, ANDed with update
   const int32_t* mesh_id;    // (N)
   const MeshInfo* meshes;
   const Cluster* clusters;
@@ -436,9 +448,6 @@ __device__ unsigned long long g_ct_prof[32];
 #define CT_COUNT(slot, v) do { } while (0)
 #endif
 
-#ifndef CT_PDL
-#define CT_PDL 0      // 1: tac_contact launched with programmatic stream serialization behind tac_geom (measured: path -0.01 ms, whole step +0.08 ms: the early-resident CTAs keep the side-stream pcl kernels off the SMs)
-#endif
 constexpr int GEOM_BLOCK = 128;
 constexpr int GEOM_MAX_CL = 512;
 constexpr int GEOM_ROUND = 256;        // faces prepared per round (2 per thread); survivors are queued in shared memory
@@ -460,12 +469,7 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(const __gr
   const int f = blockIdx.x;
   const int env = f / a.sensors_per_env;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#if CT_PDL
-  // Once every CTA of this grid has STARTED, tac_contact's CTAs may become resident on the SMs the last wave
-  // leaves idle and run their table prologue; they wait for this grid's completion before reading its results.
-  cudaTriggerProgrammaticLaunchCompletion();
-#endif
-  if (a.update && !a.update[env]) {
+  if ((a.update && !a.update[env]) || (a.update2 && !a.update2[env])) {
     if (tid == 0) a.counts[f] = -1;  // frame not rendered this step
     return;
   }
@@ -477,8 +481,9 @@ __global__ void __launch_bounds__(GEOM_BLOCK, GEOM_MIN_CTAS) tac_geom(const __gr
   if (tid == 0) {
     // ---- pose chain in f64 (xyzquat_to_tf_numpy, update_camera_pose_from_matrix, adjust_with_force)
     double q[4], R[9], Ro[9];
-    const float* fq = a.finger_quat + (size_t)f * 4;
-    const float* fp = a.finger_pos + (size_t)f * 3;
+    const int sensor = f - env * a.sensors_per_env;
+    const float* fq = a.fquat_n[sensor] + (size_t)env * a.fquat_stride;
+    const float* fp = a.fpos_n[sensor] + (size_t)env * a.fpos_stride;
     const float* oq = a.plug_quat + (size_t)env * 4;
     const float* op = a.plug_pos + (size_t)env * 3;
     auto q2m = [](const float* qq, double* m) {
@@ -742,26 +747,18 @@ struct ContactArgs {
 #ifndef CT_ZERO_BYTES
 #define CT_ZERO_BYTES 4096
 #endif
-#ifndef CT_LAZY_Z
-#define CT_LAZY_Z 1   // 1: empty z-buffer + per-fragment gel-depth lookup; 0: z-buffer initialised with the gel depth
-#endif
-#ifndef CT_ZINIT_ROWS
-#define CT_ZINIT_ROWS 0
-#endif
-#ifndef CT_ZERO_PLAIN
-#define CT_ZERO_PLAIN 0   // 1: tac_contact zeroes gel_depth with plain streaming stores instead of bulk copies
-#endif
-#ifndef CT_DYN
-#define CT_DYN 1      // 1: warps fetch their raster / shade batches from shared counters instead of a fixed stride
-#endif
-#ifndef CT_SHADE_UNROLL
-#define CT_SHADE_UNROLL 0
+#ifndef CT_EARLY_OUT
+#define CT_EARLY_OUT 1   // 1: the two exact early-outs for clipped fragments (light loop, zero-difference regions)
 #endif
 constexpr int CT_BLOCK = CT_BLOCK_N;
 constexpr int CT_CHUNK = 1024;       // triangles whose scan rows are enumerated together
 static_assert(CT_CHUNK % CT_BLOCK_N == 0, "CT_CHUNK must be a multiple of the block size");
 constexpr int CT_BUD_GRAY = CT_BUD_N;    // region pixels (interior + halo) held in shared memory, 8 B each
 constexpr int CT_BUD_RGB = 4096;     // three-channel path: + 24 B per pixel of difference / blur planes
+// Empty z-buffer entry: depth +inf in the high word, 0 in the low word.  Any fragment key (finite depth, low word
+// >= 1) is smaller; a pixel is a hit iff its low word is non-zero; and once shading reuses the two words of a pixel
+// as (difference, horizontal blur), an untouched pixel already READS as difference 0.0f - no clearing pass.
+constexpr unsigned long long CT_EMPTY = 0x7f80000000000000ull;
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -813,45 +810,46 @@ __device__ __forceinline__ void row_span(const Setup& s, float dy, float sx0, fl
   exact = sure && loB <= xlo && hiB >= xhi;
 }
 
-// One fragment: exact coverage + depth, GL_LESS against what the shared z-buffer holds (it starts
-// as the gel depth, so a peg fragment only lands where it is in front of the gel).
-// key = depth bits << 32 | (orig face << 12 | slot) + 1; the gel's key has a zero low word.
-__device__ __forceinline__ void raster_frag(float znear, const Setup& s, int k, float dx, float dy, unsigned long long* zp, int* s_hits,
-                                            const float* __restrict__ d0p) {
-#if CT_LAZY_Z
-  const float d0 = __ldg(d0p);   // issued first: its latency hides behind the edge functions and the division
-#endif
-  float e1, e2, es;
-  const float t = cover(znear, s, dx, dy, e1, e2, es);
-  if (t < 0.0f) return;
-#if CT_LAZY_Z
-  if (d0 != 0.0f && !(t < d0)) return;   // GL_LESS against the gel, which was drawn first (ties keep the gel)
-#endif
-  const unsigned long long key =
-      ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)((((uint32_t)s.orig << 12) | (uint32_t)k) + 1u);
-  if (key < *zp) {
-    atomicMin(zp, key);
-    *s_hits = 1;
+// Bounds of the pixels this lane has put a peg fragment on (image coordinates).
+struct HitBox {
+  int x0, y0, x1, y1;
+  __device__ __forceinline__ void add(int px, int py) {
+    x0 = min(x0, px); x1 = max(x1, px); y0 = min(y0, py); y1 = max(y1, py);
   }
-}
+};
 
-// Fragment of an exact span: inside by construction, only depth (N, det) and the z test.
-__device__ __forceinline__ void raster_frag_depth(float znear, V3 N, float det, uint32_t orig, int k, float dx, float dy,
-                                                  unsigned long long* zp, int* s_hits, const float* __restrict__ d0p) {
-#if CT_LAZY_Z
-  const float d0 = __ldg(d0p);
-#endif
-  const float t = __fdiv_rn(det, edge_fn(dx, dy, N));
-  if (!(t >= znear)) return;
-#if CT_LAZY_Z
+// The z test of one fragment of depth t at the shared z-buffer entry *zp: GL_LESS against the gel (drawn first,
+// d0 = its depth at this pixel, 0 = no gel: ties keep the gel), then against the peg fragments already there.
+// key = depth bits << 32 | (orig face << 12 | slot) + 1: equal depths resolve to the lower original face index.
+__device__ __forceinline__ void z_test(float t, float d0, uint32_t orig, int k, unsigned long long* zp, HitBox& hb, int px,
+                                       int py) {
   if (d0 != 0.0f && !(t < d0)) return;
-#endif
   const unsigned long long key =
       ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(((orig << 12) | (uint32_t)k) + 1u);
   if (key < *zp) {
     atomicMin(zp, key);
-    *s_hits = 1;
+    hb.add(px, py);      // a pixel that ever received a peg fragment in front of the gel stays a hit
   }
+}
+
+// One fragment: exact coverage + depth.
+__device__ __forceinline__ void raster_frag(float znear, const Setup& s, int k, float dx, float dy, unsigned long long* zp,
+                                            const float* __restrict__ d0p, HitBox& hb, int px, int py) {
+  const float d0 = __ldg(d0p);   // issued first: its latency hides behind the edge functions and the division
+  float e1, e2, es;
+  const float t = cover(znear, s, dx, dy, e1, e2, es);
+  if (t < 0.0f) return;
+  z_test(t, d0, s.orig, k, zp, hb, px, py);
+}
+
+// Fragment of an exact span: inside by construction, only depth (N, det) and the z test.
+__device__ __forceinline__ void raster_frag_depth(float znear, V3 N, float det, uint32_t orig, int k, float dx, float dy,
+                                                  unsigned long long* zp, const float* __restrict__ d0p, HitBox& hb,
+                                                  int px, int py) {
+  const float d0 = __ldg(d0p);
+  const float t = __fdiv_rn(det, edge_fn(dx, dy, N));
+  if (!(t >= znear)) return;
+  z_test(t, d0, orig, k, zp, hb, px, py);
 }
 
 template <int NCH>
@@ -870,9 +868,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   __shared__ int s_off[CT_CHUNK];
   __shared__ int s_wsum[CT_BLOCK / 32];
   __shared__ float sM[12];
-  __shared__ int s_hits, s_frame, s_next;
-  __shared__ int s_rctr, s_sctr;   // CT_DYN: next raster item / next region pixel to hand out
-  __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows)
+  __shared__ int s_frame, s_next, s_anydiff;
+  __shared__ int s_rctr, s_sctr;   // next raster item / next hit-box pixel to hand out
+  __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows whose colour changed)
   __shared__ int s_sb[4];  // bounds of the hit pixels of the current sub-window's region
   __shared__ unsigned short s_q[CT_BLOCK / 32][64];  // per-warp queue of hit pixels waiting to be shaded
   __shared__ double s_rb[511];            // remove_bg: d / 255.0 + 0.5 for d = -255..255 (f64 divide once)
@@ -884,14 +882,12 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   for (int i = tid; i < 511; i += CT_BLOCK) s_rb[i] = (double)(i - 255) / 255.0 + 0.5;
   for (int i = tid; i < CT_ZERO_BYTES / 4; i += CT_BLOCK) s_zero[i] = 0.0f;
   igi_fence_proxy_async();   // the zeros must be visible to the bulk-copy (async) proxy
-  const bool three_lights = kc.n_lights == 3;   // the allsight yaml's light count: unrolled shading path
-  (void)three_lights;
   const float span_x0 = kc.sx0, span_kx = (float)(TW - 1) / (kc.sx1 - kc.sx0);
   // gel_depth = 0 of one frame (200 704 B of zeros): a few lanes of every warp hand 4 KB pieces of the zero
   // buffer to the bulk-copy engine (shared -> global), which costs this issue-bound kernel no store
   // instructions.  Every thread commits one (possibly empty) bulk group per call.
   auto zero_fill_async = [&](int frame) {
-    if (!CT_ZERO_PLAIN && (a.fill.parts & 2) && a.fill.gel_depth && frame >= 0) {
+    if ((a.fill.parts & 2) && a.fill.gel_depth && frame >= 0) {
       constexpr int NB = TW * TH * 4 / CT_ZERO_BYTES;
       static_assert(NB * CT_ZERO_BYTES == TW * TH * 4, "zero buffer must divide the gel_depth frame");
       constexpr int PER_WARP = (NB + NW - 1) / NW;
@@ -903,11 +899,6 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     }
     igi_bulk_commit();
   };
-#if CT_PDL
-  // Programmatic dependent launch: everything above touched only constants and shared memory, so it ran while
-  // tac_geom's last CTAs were still draining; from here on its results (worklist, setups, fill) are needed.
-  cudaGridDependencySynchronize();
-#endif
   // Work items are fetched ONE FRAME AHEAD: the zero fill of the next frame is issued when the current
   // frame starts, so it has a whole frame time to land before that frame's first gel_depth write.
   if (tid == 0) {
@@ -938,9 +929,9 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     // Fused fill: the other parts of the frame's no-contact result that tac_geom left to this kernel go out
     // with plain stores while the raster / shading work of the frame runs; the barriers below order them
     // before the rewrite of the changed box.
-    if (a.fill.parts & (CT_ZERO_PLAIN ? 7 : ~2)) {
+    if (a.fill.parts & ~2) {
       FillArgs fa = a.fill;
-      if (!CT_ZERO_PLAIN) fa.parts &= ~2;
+      fa.parts &= ~2;
       fill_frame(fa, f, tid, CT_BLOCK);
     }
     if (K <= 0) continue;   // listed only to be filled
@@ -970,55 +961,22 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
         const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
         __syncthreads();
-#if CT_LAZY_Z
         // --- z-buffer starts EMPTY (two pixels per 128-bit store, no index arithmetic, no global loads); the gel's
-        // depth is looked up per fragment instead (raster_frag*: ~5700 fragments per frame against ~8000 region pixels)
+        // depth is looked up per fragment instead (~5700 fragments per frame against ~8000 region pixels)
         {
           uint4* z4 = reinterpret_cast<uint4*>(s_z);
           const int n4 = (RW * RH + 1) >> 1;
-          for (int i = tid; i < n4; i += CT_BLOCK) z4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        }
-#elif CT_ZINIT_ROWS
-        // --- z-buffer starts as the gel: a warp owns region rows warp, warp + NW, ...; no index division
-        for (int ry = warp; ry < RH; ry += NW) {
-          const int py = ry0 + ry;
-          const bool row_in = py >= cy0 && py <= cy1;
-          const float* drow = a.depth0 + py * TW + rx0;
-          unsigned long long* zrow = s_z + ry * RW;
-          for (int rx = lane; rx < RW; rx += 32) {
-            const int px = rx0 + rx;
-            const float d0 = (row_in && px >= cx0 && px <= cx1) ? __ldg(drow + rx) : 0.0f;
-            zrow[rx] = d0 != 0.0f ? (unsigned long long)__float_as_uint(d0) << 32 : ZEMPTY;
+          const uint32_t hi = (uint32_t)(CT_EMPTY >> 32);
+          for (int i = tid; i < n4; i += CT_BLOCK) z4[i] = make_uint4(0u, hi, 0u, hi);
+          if (NCH != 1) {   // three-channel path: the difference plane is separate from the keys
+            for (int i = tid; i < RW * RH * 3; i += CT_BLOCK) s_diff[i] = 0.0f;
           }
         }
-#else
-        // --- z-buffer starts as the gel (flattened over the region, 4 independent loads in flight)
-        {
-          const int npx = RW * RH;
-          const uint32_t inv_rw = 0xffffffffu / (uint32_t)RW + 1u;  // exact floor(i / RW) for i < 2^16
-          for (int i0 = tid; i0 < npx; i0 += 4 * CT_BLOCK) {
-            float d0[4];
-            bool in[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * CT_BLOCK;
-              const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
-              const int px = rx0 + rx, py = ry0 + ry;
-              in[u] = i < npx && px >= cx0 && px <= cx1 && py >= cy0 && py <= cy1;
-              d0[u] = in[u] ? __ldg(a.depth0 + py * TW + px) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = i0 + u * CT_BLOCK;
-              if (i < npx) s_z[i] = d0[u] != 0.0f ? (unsigned long long)__float_as_uint(d0[u]) << 32 : ZEMPTY;
-            }
-          }
-        }
-#endif
-        if (tid == 0) { s_hits = 0; s_sctr = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
+        if (tid == 0) { s_anydiff = 0; s_sctr = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
         CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
+        HitBox hb{TW, TH, -1, -1};
         for (int c0 = 0; c0 < K; c0 += CT_CHUNK) {
           const int kn = min(CT_CHUNK, K - c0);
           int rows[CT_CHUNK / CT_BLOCK], sum = 0;
@@ -1060,15 +1018,11 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
           __syncthreads();
           CT_T(2);
           if (tid == 0) { CT_COUNT(9, total); CT_COUNT(12, 1); CT_COUNT(13, RW * RH); CT_COUNT(14, kn); }
-#if CT_DYN
           for (;;) {
             int i0 = 0;
             if (lane == 0) i0 = atomicAdd(&s_rctr, 32);
             i0 = __shfl_sync(0xffffffffu, i0, 0);
             if (i0 >= total) break;
-#else
-          for (int i0 = warp * 32; i0 < total; i0 += CT_BLOCK) {
-#endif
             const int i = i0 + lane;
             int k = 0, py = 0, xlo = 0, xhi = -1, exact = 1;
             Setup s;
@@ -1093,8 +1047,8 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
               for (int u = 0; u < 2; ++u) {
                 const int px = xlo + u;
                 if (px <= xhi) {
-                  if (ex) raster_frag_depth(kc.znear, s.N, s.det, s.orig, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
-                  else raster_frag(kc.znear, s, k, s_dxp[px], dy, zrow + px, &s_hits, a.depth0 + py * TW + px);
+                  if (ex) raster_frag_depth(kc.znear, s.N, s.det, s.orig, k, s_dxp[px], dy, zrow + px, a.depth0 + py * TW + px, hb, px, py);
+                  else raster_frag(kc.znear, s, k, s_dxp[px], dy, zrow + px, a.depth0 + py * TW + px, hb, px, py);
                 }
               }
               xlo += 2;
@@ -1130,29 +1084,41 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
                   const uint4* q4 = reinterpret_cast<const uint4*>(list + kk);
                   const uint4 u2 = __ldg(q4 + 2), u3 = __ldg(q4 + 3);
                   const V3 N{__uint_as_float(u2.y), __uint_as_float(u2.z), __uint_as_float(u2.w)};
-                  raster_frag_depth(kc.znear, N, __uint_as_float(u3.x), u3.w, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
+                  raster_frag_depth(kc.znear, N, __uint_as_float(u3.x), u3.w, kk, dx, dy, zp, a.depth0 + yy * TW + px, hb, px, yy);
                 } else {
                   const Setup ss = load_setup(list + kk);
-                  raster_frag(kc.znear, ss, kk, dx, dy, zp, &s_hits, a.depth0 + yy * TW + px);
+                  raster_frag(kc.znear, ss, kk, dx, dy, zp, a.depth0 + yy * TW + px, hb, px, yy);
                 }
               }
             }
           }
         }
+        // bounds of the hit pixels of this region (one shared-memory atomic per warp and bound)
+        if (__any_sync(0xffffffffu, hb.x1 >= 0)) {
+          const int x0 = __reduce_min_sync(0xffffffffu, hb.x0), x1 = __reduce_max_sync(0xffffffffu, hb.x1);
+          const int y0 = __reduce_min_sync(0xffffffffu, hb.y0), y1 = __reduce_max_sync(0xffffffffu, hb.y1);
+          if (lane == 0) {
+            atomicMin(&s_sb[0], x0); atomicMax(&s_sb[2], x1);
+            atomicMin(&s_sb[1], y0); atomicMax(&s_sb[3], y1);
+          }
+        }
         igi_bulk_wait1();   // this frame's zero fill has landed; only the next frame's group may still be in flight
         __syncthreads();
         CT_T(3);
-        if (s_hits == 0) continue;  // nothing of the peg is visible here: fill already wrote the result
-        // --- shade hits, build the scaled difference image (0 where the gel is visible).  Each warp
-        // scans 32 region pixels at a time, queues the hit ones and shades a full warp of them
-        // whenever 32 are waiting, so the long shading path runs with all lanes active.
+        if (s_sb[2] < 0) continue;  // nothing of the peg is visible here: fill already wrote the result
+        // --- shade hits, build the scaled difference image (0 where the gel is visible).  Only the box of the hit
+        // pixels is scanned; each warp takes 32 box pixels at a time, queues the hit ones and shades a full warp of
+        // them whenever 32 are waiting, so the long shading path runs with all lanes active.
+        const int hbx0 = s_sb[0], hby0 = s_sb[1], hbx1 = s_sb[2], hby1 = s_sb[3];
         {
-          const int npx = RW * RH;
-          const uint32_t inv_rw = 0xffffffffu / (uint32_t)RW + 1u;
+          const int bw = hbx1 - hbx0 + 1, npx = bw * (hby1 - hby0 + 1);
+          const uint32_t inv_bw = 0xffffffffu / (uint32_t)bw + 1u;   // wraps to 0 for bw == 1
+          const uint32_t inv_rw = 0xffffffffu / (uint32_t)RW + 1u;   // exact floor(i / RW) for i < 2^16
           unsigned short* q = s_q[warp];
           int qn = 0;
-          int hx0 = TW, hx1 = -1, hy0 = TH, hy1 = -1;
-          auto shade_px = [&](int i) {
+          bool nz_any = false;
+          // all 32 lanes run the arithmetic (warp-uniform early-out votes inside shade_t); `act` gates the writes
+          auto shade_px = [&](int i, bool act) {
             const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
             const int px = rx0 + rx, py = ry0 + ry;
             const unsigned long long key = s_z[i];
@@ -1179,38 +1145,32 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             }
             V3 pp{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
-#if CT_SHADE_UNROLL
-            if (three_lights) shade_t<NCH, 3>(kc, pp, n, rgb); else shade_t<NCH, 0>(kc, pp, n, rgb);
-#else
-            shade_t<NCH, 0>(kc, pp, n, rgb);
-#endif
+            shade_t<NCH, 0, CT_EARLY_OUT != 0>(kc, pp, n, rgb);
+            if (!act) return;
             const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
             // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
             if (px >= tx && px <= ix1 && py >= ty && py <= iy1)
               gdep[py * TW + px] = sub(__ldg(a.depth0 + py * TW + px), t);
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = (float)((int)rgb[c] - (int)bs[c]) * kc.calib_scale;
-            hx0 = min(hx0, px); hx1 = max(hx1, px); hy0 = min(hy0, py); hy1 = max(hy1, py);
+            for (int c = 0; c < NCH; ++c) {
+              const int d = (int)rgb[c] - (int)bs[c];
+              nz_any = nz_any || d != 0;
+              s_diff[DS * i + c] = (float)d * kc.calib_scale;
+            }
             CT_COUNT(11, 1);
           };
-#if CT_DYN
           for (;;) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_sctr, 32);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= npx) break;
-#else
-          for (int base = warp * 32; base < npx; base += CT_BLOCK) {
-#endif
-            const int i = base + lane;
+            const int j = base + lane;
             bool hit = false;
-            if (i < npx) {
-              const unsigned long long key = s_z[i];
-              hit = key != ZEMPTY && (uint32_t)key != 0u;
-              if (!hit) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) s_diff[DS * i + c] = 0.f;
-              }
+            int i = 0;
+            if (j < npx) {
+              const int by = bw == 1 ? j : (int)__umulhi((uint32_t)j, inv_bw), bx = j - by * bw;
+              i = (hby0 + by - ry0) * RW + (hbx0 + bx - rx0);
+              hit = (uint32_t)s_z[i] != 0u;     // low word: 0 = no peg fragment here (reads as difference 0)
             }
             const unsigned bm = __ballot_sync(0xffffffffu, hit);
             if (hit) q[qn + __popc(bm & ((1u << lane) - 1u))] = (unsigned short)i;
@@ -1220,28 +1180,27 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
               qn -= 32;
               const int idx = q[qn + lane];
               __syncwarp();
-              shade_px(idx);
+              shade_px(idx, true);
             }
           }
-          if (lane < qn) shade_px(q[lane]);
-          if (__any_sync(0xffffffffu, hx1 >= 0)) {
-            hx0 = __reduce_min_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1);
-            hy0 = __reduce_min_sync(0xffffffffu, hy0); hy1 = __reduce_max_sync(0xffffffffu, hy1);
-            if (lane == 0) {
-              atomicMin(&s_sb[0], hx0); atomicMax(&s_sb[2], hx1);
-              atomicMin(&s_sb[1], hy0); atomicMax(&s_sb[3], hy1);
-            }
-          }
+          if (qn > 0) shade_px(q[lane < qn ? lane : 0], lane < qn);
+          if (__any_sync(0xffffffffu, nz_any) && lane == 0) s_anydiff = 1;
         }
         __syncthreads();
         CT_T(4);
+#if CT_EARLY_OUT
+        // Every shaded pixel equals the simulated background (e.g. both clip at 255 under the inverse-square light
+        // model): the difference image is identically 0, so the calibrated colour is the real background frame the
+        // fill already wrote and the observation is the empty one.  Exact, not an approximation.
+        if (!s_anydiff) continue;
+#endif
         // Only pixels within the blur radius of a hit can differ from what tac_fill wrote (the difference
         // image is 0 elsewhere): the changed box = hit box dilated by HALO, inside the interior.
-        const int bx0 = max(s_sb[0] - HALO, tx), bx1 = min(s_sb[2] + HALO, ix1);
-        const int by0 = max(s_sb[1] - HALO, ty), by1 = min(s_sb[3] + HALO, iy1);
+        const int bx0 = max(hbx0 - HALO, tx), bx1 = min(hbx1 + HALO, ix1);
+        const int by0 = max(hby0 - HALO, ty), by1 = min(hby1 + HALO, iy1);
         if (tid == 0) {
-          s_hb[0] = min(s_hb[0], s_sb[0]); s_hb[1] = min(s_hb[1], s_sb[1]);
-          s_hb[2] = max(s_hb[2], s_sb[2]); s_hb[3] = max(s_hb[3], s_sb[3]);
+          s_hb[0] = min(s_hb[0], hbx0); s_hb[1] = min(s_hb[1], hby0);
+          s_hb[2] = max(s_hb[2], hbx1); s_hb[3] = max(s_hb[3], hby1);
         }
         if (bx0 > bx1 || by0 > by1) continue;   // hits only in this region's halo: they belong to a neighbour
         // --- 7-tap horizontal pass over the changed columns (BORDER_REFLECT_101 at the image edge), for the
@@ -1526,8 +1485,13 @@ extern "C" int igi_tactile_render(const IgiSensorParams* sensor, const IgiTactil
                                   void* stream) {
   IGI_REQUIRE(sensor && m && st && fr && sc && out, "igi_tactile_render: null struct");
   IGI_REQUIRE(fr->n_envs >= 0 && fr->sensors_per_env >= 1, "igi_tactile_render: bad frame counts");
-  IGI_REQUIRE(fr->finger_pos && fr->finger_quat && fr->plug_pos && fr->plug_quat && fr->mesh_id && fr->bg_id,
-              "igi_tactile_render: null pose pointer");
+  IGI_REQUIRE(fr->sensors_per_env <= 8, "igi_tactile_render: at most 8 sensors per env");
+  IGI_REQUIRE(fr->plug_pos && fr->plug_quat && fr->mesh_id && fr->bg_id, "igi_tactile_render: null pose pointer");
+  for (int n = 0; n < fr->sensors_per_env; ++n)
+    IGI_REQUIRE((fr->finger_pos || fr->finger_pos_n[n]) && (fr->finger_quat || fr->finger_quat_n[n]),
+                "igi_tactile_render: null fingertip pose pointer");
+  IGI_REQUIRE((fr->finger_pos || fr->finger_pos_stride >= 3) && (fr->finger_quat || fr->finger_quat_stride >= 4),
+              "igi_tactile_render: per-sensor fingertip views need their env strides");
   IGI_REQUIRE(m->verts && m->vnorm && m->faces && m->face_orig && m->meshes && m->clusters,
               "igi_tactile_render: null mesh pointer");
   IGI_REQUIRE(st->depth0 && st->bg_sim && st->bg_real && st->obs_empty && st->grid && st->hiz && st->dxp && st->dyp,
@@ -1574,8 +1538,14 @@ extern "C" int igi_tactile_render(const IgiSensorParams* sensor, const IgiTactil
   fa.n_frames = F;
   fa.parts = 7;
   GeomArgs g{};
-  g.finger_pos = fr->finger_pos; g.finger_quat = fr->finger_quat; g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
-  g.force = fr->force; g.update = fr->update; g.mesh_id = fr->mesh_id;
+  g.plug_pos = fr->plug_pos; g.plug_quat = fr->plug_quat;
+  for (int n = 0; n < fr->sensors_per_env; ++n) {
+    g.fpos_n[n] = fr->finger_pos ? fr->finger_pos + 3 * n : fr->finger_pos_n[n];
+    g.fquat_n[n] = fr->finger_quat ? fr->finger_quat + 4 * n : fr->finger_quat_n[n];
+  }
+  g.fpos_stride = fr->finger_pos ? 3 * fr->sensors_per_env : fr->finger_pos_stride;
+  g.fquat_stride = fr->finger_quat ? 4 * fr->sensors_per_env : fr->finger_quat_stride;
+  g.force = fr->force; g.update = fr->update; g.update2 = fr->update2; g.mesh_id = fr->mesh_id;
   g.meshes = (const MeshInfo*)m->meshes; g.clusters = (const Cluster*)m->clusters;
   g.verts = m->verts; g.faces = m->faces; g.face_orig = m->face_orig; g.grid = st->grid; g.hiz = st->hiz; g.depth0 = st->depth0;
   g.dxp = st->dxp; g.dyp = st->dyp;
@@ -1623,25 +1593,8 @@ extern "C" int igi_tactile_render(const IgiSensorParams* sensor, const IgiTactil
       IGI_CUDA(cudaFuncSetAttribute(tac_contact<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rgb));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-#if CT_PDL
-    {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(gray ? min(F, sms * CT_CTAS) : min(F, sms)));
-      cfg.blockDim = dim3(CT_BLOCK);
-      cfg.dynamicSmemBytes = gray ? smem_gray : smem_rgb;
-      cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      if (gray) IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<1>, kc, ca));
-      else IGI_CUDA(cudaLaunchKernelEx(&cfg, tac_contact<3>, kc, ca));
-    }
-#else
     if (gray) tac_contact<1><<<min(F, sms * CT_CTAS), CT_BLOCK, smem_gray, s>>>(kc, ca);
     else tac_contact<3><<<min(F, sms), CT_BLOCK, smem_rgb, s>>>(kc, ca);
-#endif
     IGI_CHECK_LAUNCH("tac_contact");
   }
   return IGI_OK;

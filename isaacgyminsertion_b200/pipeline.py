@@ -84,8 +84,7 @@ class HostObsPipeline:
         task.cam_renders, task.seg_renders = d["depth"], d["seg"]
         up = self._ones if update is None else update
         if task.pcl_cam and self.socket_every_step:
-            task._socket_pending = True
-            task.got_socket.zero_()
+            task.invalidate_socket_cache()
         task.compute_observations(up, up, up, up, up, self._zeros, self._zeros)
         self.d_out[slot].copy_(task.obs_packed)
         self.ev_done[slot].record(cur)

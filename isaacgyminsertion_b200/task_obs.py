@@ -16,10 +16,13 @@ tactile_imgs and pcl are two views of ONE packed row [3*2048 | 2400] per env
 (`obs_packed`), so the multi-GPU all-gather (dist.py) sends the kernels' output buffer
 directly, with no pack step.
 """
+import ctypes as _c
+
 import numpy as np
 import torch
 from scipy.spatial.transform import Rotation as R
 
+from . import _lib
 from .allsight_render import BatchedAllSight, OBS_LEN
 from .pcl_utils import CameraPointCloud, filter_pts
 
@@ -89,6 +92,11 @@ class FactoryTaskInsertionTactileObs:
         self._all_pts = (torch.zeros((N, self.total_points, 3), dtype=torch.float32, device=dev)
                          if self.include_all_pcl else None)
         self._socket_pending = True        # host mirror of `not self.got_socket.all()` (no sync)
+        self._socket_force = False         # invalidate_socket_cache(): treat every env as restarted
+        self._lib = _lib.load()
+        self._upd_seg = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._upd_pcl = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._restarted = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.pcl_pos_noise = torch.randn(N, 1, 3, device=dev)
         self.rot_pcl_angle = torch.zeros(N, device=dev)
         self.rot_axes = torch.zeros(N, dtype=torch.long, device=dev)
@@ -127,15 +135,30 @@ class FactoryTaskInsertionTactileObs:
 
     @torch.no_grad()
     def update_tactile(self, update_freq, update_delay):
-        """factory_task_insertion.py:479-513, poses stay on the device in f32."""
-        fpos = torch.stack((self.left_finger_pos, self.right_finger_pos, self.middle_finger_pos), dim=1).contiguous()
-        fquat = torch.stack((self.left_finger_quat, self.right_finger_quat, self.middle_finger_quat), dim=1).contiguous()
-        update = torch.logical_and(update_freq, update_delay)
+        """factory_task_insertion.py:479-513, poses stay on the device in f32.  Two launches of this library's
+        kernels + the queue push; the fingertip views and the two masks are passed as they are (no stack /
+        logical_and / copy launches)."""
+        fpos = (self.left_finger_pos, self.right_finger_pos, self.middle_finger_pos)
+        fquat = (self.left_finger_quat, self.right_finger_quat, self.middle_finger_quat)
         force = (100 * self.finger_normalized_forces) if self.tactile_wrt_force else None   # :532-535
-        self.tactile_engine.render(fpos, fquat, self.plug_pos.contiguous(), self.plug_quat.contiguous(),
-                                   force=force, update=update, obs_out=self.tactile_imgs)
-        self.tactile_queue[:, 1:] = self.tactile_queue[:, :-1].clone().detach()
-        self.tactile_queue[:, 0, ...] = self.tactile_imgs
+        self.tactile_engine.render(fpos, fquat, self._dense(self.plug_pos), self._dense(self.plug_quat),
+                                   force=force, update=update_freq, update2=update_delay, obs_out=self.tactile_imgs)
+        # tactile_queue[:, 1:] = tactile_queue[:, :-1]; tactile_queue[:, 0] = tactile_imgs   (:512-513)
+        _lib.check(self._lib.igi_queue_push(
+            _c.c_void_p(self.tactile_queue.data_ptr()), _c.c_void_p(self.tactile_imgs.data_ptr()), _c.c_int(0),
+            _c.c_int64(self.obs_packed.stride(0)), _c.c_int(self.num_envs), _c.c_int(self.tactile_queue.shape[1]),
+            _c.c_longlong(TACTILE_FLOATS), _lib.stream_ptr(self.device)), "igi_queue_push")
+
+    @staticmethod
+    def _dense(t):
+        return t if t.is_contiguous() and t.dtype == torch.float32 else t.contiguous().float()
+
+    @staticmethod
+    def _u8(m):
+        """bool (1 byte per env) / uint8 mask -> contiguous uint8 tensor without a copy when possible."""
+        if m.dtype == torch.bool and m.is_contiguous():
+            return m.view(torch.uint8)
+        return m.to(torch.uint8).contiguous()
 
     @torch.no_grad()
     def _render_tactile(self, left_finger_pose, right_finger_pose, middle_finger_pose, object_pose, update_freq,
@@ -157,12 +180,27 @@ class FactoryTaskInsertionTactileObs:
     @torch.no_grad()
     def update_external_cam(self, update_freq, update_delay, seg_update_delay, seg_noise, pcl_noise):
         """factory_task_insertion.py:896-1056 (cam_type 'd', seg_cam + pcl_cam, merge_socket_pcl,
-        include_plug_pcl — the shipped student configuration)."""
-        update = torch.logical_and(update_freq, update_delay)
-        update_seg = torch.logical_and(update_freq, seg_update_delay)
+        include_plug_pcl — the shipped student configuration).  Steady state = 5 launches of this library's
+        kernels (masks, seg_buf rows, compaction, FPS, assemble + queue) and no eager torch op."""
         depth, seg = self.cam_renders, self.seg_renders
-        N = self.num_envs
-        self.seg_buf = torch.where(update_seg[:, None], seg.reshape(N, -1), self.seg_buf)            # :934-940
+        N, dev, lib = self.num_envs, self.device, self._lib
+        st = _lib.stream_ptr(dev)
+        compute_socket = bool(self._socket_pending)
+        f, d, sd = self._u8(update_freq), self._u8(update_delay), self._u8(seg_update_delay)
+        # upd_seg = freq & seg_delay; restarted = socket pending & got_socket == 0 (-> 1); upd_pcl = freq & delay | restarted
+        _lib.check(lib.igi_cam_masks(
+            _c.c_void_p(f.data_ptr()), _c.c_void_p(d.data_ptr()), _c.c_void_p(sd.data_ptr()),
+            _c.c_void_p(self.got_socket.data_ptr()), _c.c_int((2 if self._socket_force else 1) if compute_socket else 0),
+            _c.c_void_p(self._upd_seg.data_ptr()), _c.c_void_p(self._upd_pcl.data_ptr()),
+            _c.c_void_p(self._restarted.data_ptr()), _c.c_int(N), st), "igi_cam_masks")
+        segf = seg.reshape(N, -1)
+        if segf.dtype != torch.int32 or not segf.is_contiguous():
+            segf = segf.to(torch.int32).contiguous()
+        row = self.seg_buf.shape[1] * 4
+        _lib.check(lib.igi_copy_rows_where(                                                        # :934-940
+            _c.c_void_p(self.seg_buf.data_ptr()), _c.c_longlong(row), _c.c_void_p(segf.data_ptr()), _c.c_longlong(row),
+            _c.c_void_p(self._upd_seg.data_ptr()), _c.c_int(1), _c.c_longlong(N), _c.c_longlong(row), st),
+            "igi_copy_rows_where")
         gen = self.pcl_generator
         box = filter_pts.box
         all_pts = None
@@ -175,7 +213,6 @@ class FactoryTaskInsertionTactileObs:
             if self.pcl_noise_enabled:
                 all_pts = torch.where(pcl_noise[:, None, None], self.pcl_process.augment(
                     all_pts, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), all_pts)
-        compute_socket = self._socket_pending
         pts, cnt, any_ = gen.engine.compact(depth, seg, (2, 3) if compute_socket else (2,), box)     # :956-959,975
         fused = compute_socket and self.sampler == "fps" and self._both_pts is not None
         if fused:    # plug and socket tasks in one size-ordered launch
@@ -183,30 +220,35 @@ class FactoryTaskInsertionTactileObs:
         else:
             self._sample(pts, cnt, any_, 0, self.num_points, self._plug_pts)                         # :961-964
         plug_pts = self._plug_pts
-        noisy = pcl_noise.clone()
-        if self.pcl_noise_enabled:
-            plug_pts = torch.where(noisy[:, None, None], self.pcl_process.augment(
+        if self.pcl_noise_enabled:       # RNG-defined augmentation: torch ops, off in the shipped path
+            plug_pts = torch.where(pcl_noise[:, None, None], self.pcl_process.augment(
                 plug_pts, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), plug_pts)          # :966-969
         if compute_socket:                                                                          # :972-989
             if not fused:
                 self._sample(pts, cnt, any_, 1, self.num_points_socket, self.socket_pcl)
-            restarted = self.got_socket[:, 0] == 0
-            noisy = noisy | restarted
             if self.pcl_noise_enabled:
+                noisy = pcl_noise | self._restarted.bool()
                 self.socket_pcl.copy_(torch.where(noisy[:, None, None], self.pcl_process.augment(
                     self.socket_pcl, self.rot_pcl_angle, self.rot_axes, self.pcl_pos_noise), self.socket_pcl))
-            self.got_socket.masked_fill_(restarted[:, None], 1)      # no boolean-index host sync
-            update = update | restarted
             self._socket_pending = False
+            self._socket_force = False
         if all_pts is not None:
             merged = torch.cat([plug_pts, self.socket_pcl, all_pts], dim=1).flatten(start_dim=1)     # :1014-1027
         elif plug_pts is self._plug_pts and self._both_pts is not None:
             merged = self._both_pts.view(N, -1)
         else:
             merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)
-        self.pcl.copy_(torch.where(update[:, None], merged, self.pcl))
-        self.pcl_queue[:, 1:] = self.pcl_queue[:, :-1].clone().detach()                              # :1046-1048
-        self.pcl_queue[:, 0, ...] = self.pcl
+        # pcl[update] = merged[update] (:1027); pcl_queue[:, 1:] = pcl_queue[:, :-1]; pcl_queue[:, 0] = pcl (:1046-1048)
+        _lib.check(lib.igi_pcl_assemble(
+            _c.c_void_p(merged.data_ptr()), _c.c_int64(merged.stride(0)), _c.c_void_p(self.pcl.data_ptr()),
+            _c.c_int64(self.pcl.stride(0)), _c.c_void_p(self._upd_pcl.data_ptr()), _c.c_void_p(self.pcl_queue.data_ptr()),
+            _c.c_int(N), _c.c_int(self.pcl_queue.shape[1]), _c.c_longlong(self.pcl_floats), st), "igi_pcl_assemble")
+
+    def invalidate_socket_cache(self):
+        """Every env recomputes its socket cloud on the next step (what a reset of all envs does to got_socket),
+        without a fill launch: the masks kernel is told to treat every env as restarted."""
+        self._socket_pending = True
+        self._socket_force = True
 
     # ------------------------------------------------------------------ both parts of one env step
     @torch.no_grad()
