@@ -1,14 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the observation hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--sampler fps|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config obs4096|tactile1024|pcl1024|sweep|small]
+                  [--envs E] [--scaling weak|strong] [--falloff inverse_square|none] [--gather p2p|nccl]
   python bench.py --impl reference ...      # the CPU oracle on the host cores
 
 A "step" = one pass of the visuotactile observation path over E envs per GPU:
 E x 3 tactile frames (224x224 render -> 2048-float obs) + E point-cloud observations
-(96x54 depth+seg -> 400 plug + 400 socket points), followed for N > 1 by the NCCL all-gather
-of the packed observation rows.  Unit: obs/s, 1 obs = one env's 3 tactile frames + 1 cloud.
-Scaling is weak (E envs per GPU).  Inputs are synthetic (IsaacGym is a closed dependency).
+(96x54 depth+seg -> 400 plug + 400 socket points), followed for N > 1 by the gather of the packed
+observation rows onto the learner rank.  Unit: obs/s, 1 obs = one env's 3 tactile frames + 1 cloud.
+Inputs are synthetic (IsaacGym is a closed dependency).
+
+Configurations (BASELINE.json `configs`):
+  obs4096     (default) config 4/5 headline: 4096 envs per GPU (weak scaling) or 4096 envs in total sharded
+              over the ranks (`--scaling strong`, config 4 as written: 512 envs/rank at 8 GPUs)
+  tactile1024 config 2: tactile path alone, 1024 envs
+  pcl1024     config 3: point-cloud path alone, 1024 envs
+  sweep       config 5: resident step at 256 ... 16384 envs per GPU, one JSON line with a `sweep` array
+  small       the reference's own operating points (10 and 256 envs, scripts/train_s3.sh:5, train_s2.sh:5):
+              eager launches and the CUDA-graph replay of the step
 """
 import argparse
 import json
@@ -31,6 +41,7 @@ TACTILE_BYTES_PER_FRAME = 861312      # SURVEY.md 8d / BASELINE.md 4
 PCL_BYTES_PER_ENV_FPS = 51200
 PCL_BYTES_PER_ENV_REF = 57600
 FILL_BYTES_PER_FRAME = 150528 + 200704 + 8192   # color, gel_depth, obs written (bg_real / obs_empty sources are L2-resident)
+SWEEP_ENVS = (256, 512, 1024, 2048, 4096, 8192, 16384)
 
 
 def parse():
@@ -38,14 +49,23 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--config", default="obs4096", choices=["obs4096", "tactile1024", "pcl1024", "sweep", "small"])
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (weak) / in total (strong); default from --config")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--sampler", default="fps", choices=["fps", "reference"])
+    ap.add_argument("--falloff", default=None, choices=["inverse_square", "none"],
+                    help="light model (DESIGN.md 'light model'); default = the shipped yaml (inverse_square)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: copy-engine peer copies into the learner's buffer (default) or NCCL all-gather")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sync-gather", action="store_true", help="do not overlap the all-gather with the next step")
+    ap.add_argument("--no-components", action="store_true", help="skip the per-kernel timings / roofline block")
+    ap.add_argument("--no-alt-falloff", action="store_true", help="skip the second resident leg under the other light model")
+    ap.add_argument("--sync-gather", action="store_true", help="wait for every step's gather before the next step")
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
     ap.add_argument("--no-overlap", action="store_true", help="point-cloud path on the same stream as the tactile path")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -177,6 +197,11 @@ def build_oracle():
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
 
 
+CPU_SCENE_NOTE = ("oracle scene per frame = posed peg + the 21 824 gel triangles that can reach the in-gel camera "
+                  "(of the reference's 231 146-triangle gel mesh, which pyrender submits whole): the port does LESS work "
+                  "than the reference would, so GPU / CPU ratios built on it are conservative")
+
+
 def cpu_baseline_serial(gym, P, depth, seg, n):
     """The oracle's serial per-env loop on ONE host core (reference structure)."""
     build_oracle()
@@ -189,7 +214,7 @@ def cpu_baseline_serial(gym, P, depth, seg, n):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{n} envs (={3 * n} tactile frames + {n} plug+socket clouds), serial oracle loop, "
-                      f"{dt:.2f} s; whole scene (gel + peg) rasterised per frame like the reference"}
+                      f"{dt:.2f} s; " + CPU_SCENE_NOTE}
 
 
 def run_reference(args):
@@ -216,12 +241,13 @@ def run_reference(args):
             pool.map(_cpu_env, jobs, chunksize=max(n // cores, 1))
         dt = time.perf_counter() - t0
     value = n * args.steps / dt
+    envs = args.envs or 4096
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"visuotactile obs, bounded sample of {n} envs per step (same generators as the "
-                               f"{args.envs}-env GPU workload)", "envs_per_step": n},
+                               f"{envs}-env GPU workload)", "envs_per_step": n, "scene": CPU_SCENE_NOTE},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} envs/step x {args.steps} steps, {cores} worker processes"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -233,6 +259,46 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+class Workload:
+    """One rank's task object + device-resident inputs + pinned host copies of them."""
+
+    def __init__(self, E, offset, total, dev, args, tactile=True, pcl=True, falloff=None, pin=True):
+        import torch
+        from isaacgyminsertion_b200.task_obs import FactoryTaskInsertionTactileObs
+        self.E, self.dev = E, dev
+        self.gym, self.P, self.depth_np, self.seg_np = make_inputs(E, offset, total)
+        P = self.P
+        self.task = FactoryTaskInsertionTactileObs(
+            E, self.gym, P["mesh_id"], P["bg_id"], device=dev, sampler=args.sampler, strict_rng=False,
+            overlap_streams=not args.no_overlap, tactile=tactile, pcl_cam=pcl, falloff=falloff,
+            global_env_offset=offset, total_envs=total)
+
+        def host(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            return t.pin_memory() if pin else t
+        self.h = dict(fpos=host(P["finger_pos"]), fquat=host(P["finger_quat"]), ppos=host(P["plug_pos"]),
+                      pquat=host(P["plug_quat"]), depth=host(self.depth_np), seg=host(self.seg_np))
+        self.d = {k: v.to(dev) for k, v in self.h.items()}
+        self.ones = torch.ones(E, dtype=torch.bool, device=dev)
+        self.zeros = torch.zeros(E, dtype=torch.bool, device=dev)
+        self.load_state()
+
+    def load_state(self):
+        t, d = self.task, self.d
+        t.left_finger_pos, t.right_finger_pos, t.middle_finger_pos = d["fpos"][:, 0], d["fpos"][:, 1], d["fpos"][:, 2]
+        t.left_finger_quat, t.right_finger_quat, t.middle_finger_quat = d["fquat"][:, 0], d["fquat"][:, 1], d["fquat"][:, 2]
+        t.plug_pos, t.plug_quat = d["ppos"], d["pquat"]
+        t.cam_renders, t.seg_renders = d["depth"], d["seg"]
+
+    def step(self):
+        t = self.task
+        if t.pcl_cam:
+            t.invalidate_socket_cache()   # worst case: every env restarted -> socket cloud recomputed each step
+        # update_tactile + update_external_cam with the reference's mask arguments (task :862-887)
+        o, z = self.ones, self.zeros
+        t.compute_observations(o, o, o, o, o, z, z)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -246,73 +312,25 @@ def main():
     os.dup2(2, 1)
     import torch
     import torch.distributed as dist
+    from isaacgyminsertion_b200 import _lib
     from isaacgyminsertion_b200 import dist as igdist
-    from isaacgyminsertion_b200.task_obs import FactoryTaskInsertionTactileObs
 
     rank, local_rank, world = igdist.init_from_env()
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    E = args.envs
-    total = E * world
-    gym, P, depth_np, seg_np = make_inputs(E, rank * E, total)
-    task = FactoryTaskInsertionTactileObs(E, gym, P["mesh_id"], P["bg_id"], device=dev, sampler=args.sampler,
-                                          strict_rng=False, overlap_streams=not args.no_overlap)
+    numa = None if args.no_numa else igdist.bind_to_gpu_numa(local_rank)   # before any pinned allocation
+    lib = _lib.load()
 
-    # pinned host staging (the e2e leg copies from / to these every step)
-    def pin(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_fpos, h_fquat = pin(P["finger_pos"]), pin(P["finger_quat"])
-    h_ppos, h_pquat = pin(P["plug_pos"]), pin(P["plug_quat"])
-    h_depth, h_seg = pin(depth_np), pin(seg_np)
-    h_out = torch.empty(task.obs_packed.shape, dtype=torch.float32).pin_memory()
-    d_fpos, d_fquat = h_fpos.to(dev), h_fquat.to(dev)
-    d_depth, d_seg = h_depth.to(dev), h_seg.to(dev)
-    ones = torch.ones(E, dtype=torch.bool, device=dev)
-    zeros = torch.zeros(E, dtype=torch.bool, device=dev)
-
-    def load_state(fpos, fquat, ppos, pquat, depth, seg):
-        task.left_finger_pos, task.right_finger_pos, task.middle_finger_pos = fpos[:, 0], fpos[:, 1], fpos[:, 2]
-        task.left_finger_quat, task.right_finger_quat, task.middle_finger_quat = fquat[:, 0], fquat[:, 1], fquat[:, 2]
-        task.plug_pos, task.plug_quat = ppos, pquat
-        task.cam_renders, task.seg_renders = depth, seg
-
-    load_state(d_fpos, d_fquat, h_ppos.to(dev), h_pquat.to(dev), d_depth, d_seg)
-
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gathered = [torch.empty((total, task.obs_packed.shape[1]), dtype=torch.float32, device=dev) for _ in range(2)] \
-        if world > 1 else None
-    send = [torch.empty_like(task.obs_packed) for _ in range(2)] if world > 1 else None
-    pending = [None]
-
-    def obs_gather(i):
-        if args.sync_gather:
-            dist.all_gather_into_tensor(gathered[0], task.obs_packed)
-        else:
-            # double-buffered: the gather of step i overlaps the kernels of step i+1
-            buf = send[i & 1]
-            buf.copy_(task.obs_packed)
-            ev = torch.cuda.Event()
-            ev.record()
-            if pending[0] is not None:
-                pending[0].wait()
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                pending[0] = dist.all_gather_into_tensor(gathered[i & 1], buf, async_op=True)
-
-    def obs_step(i):
-        task.invalidate_socket_cache()   # worst case: every env restarted -> socket cloud recomputed each step
-        # update_tactile + update_external_cam with the reference's mask arguments (task :862-887)
-        task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
-        if world > 1:
-            obs_gather(i)
-
-    def finish():
-        if world > 1 and pending[0] is not None:
-            pending[0].wait()
-            torch.cuda.current_stream().wait_stream(comm_stream)
-            pending[0] = None
+    cfg = args.config
+    tactile, pcl = cfg != "pcl1024", cfg != "tactile1024"
+    envs = args.envs or (1024 if cfg in ("tactile1024", "pcl1024") else 4096)
+    if args.scaling == "strong":
+        lo, hi = igdist.env_slice(envs, rank, world)
+        E, offset, total = hi - lo, lo, envs
+    else:
+        E, offset, total = envs, rank * envs, envs * world
 
     def barrier():
         if world > 1:
@@ -324,15 +342,13 @@ def main():
             fn(i)
         if after:
             after()
-        finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(i)
         if after:
-            after()      # drains the copy streams: every step's host result has landed
-        finish()
+            after()      # drains the copy / gather streams: every step's result has landed
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -343,132 +359,220 @@ def main():
         return ms
 
     W = max(args.warmup, 3)
-    from isaacgyminsertion_b200 import _lib
-    lib = _lib.load()
+
+    # ---- sweep / small: resident step at several sizes, one line -------------------------------------------
+    if cfg in ("sweep", "small"):
+        from isaacgyminsertion_b200.pipeline import GraphedObsStep
+        sizes = SWEEP_ENVS if cfg == "sweep" else (10, 256)
+        rows = []
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        launches = 0
+        for n in sizes:
+            wl = Workload(n, rank * n, n * world, dev, args, falloff=args.falloff, pin=False)
+            l0 = lib.igi_launch_count()
+            ms = timed(lambda i: wl.step(), args.steps, W) / args.steps
+            per_step = (lib.igi_launch_count() - l0) // (args.steps + W)
+            launches += per_step * args.steps
+            row = {"envs_per_gpu": n, "ms_per_step": ms, "obs_per_s": n * world / (ms * 1e-3), "launches_per_step": int(per_step)}
+            if n <= 1024:
+                g = GraphedObsStep(wl.task, socket_every_step=True)
+                row["graph_ms_per_step"] = timed(lambda i: g(), args.steps, W) / args.steps
+                row["graph_obs_per_s"] = n * world / (row["graph_ms_per_step"] * 1e-3)
+                g.check_overflow()
+            wl.task.tactile_engine.check_overflow()
+            rows.append(row)
+            del wl
+            torch.cuda.empty_cache()
+        sampler.stop_flag = True
+        head = next((r for r in rows if r["envs_per_gpu"] == 4096), rows[-1])
+        if rank == 0:
+            line = {"metric": METRIC, "value": head["obs_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": W, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"FactoryTaskInsertionTactile visuotactile obs, resident step at "
+                                           f"{list(sizes)} envs per GPU (value = the {head['envs_per_gpu']}-env point)",
+                               "sweep": cfg, "sampler": args.sampler, "falloff": args.falloff or "inverse_square",
+                               "gather": "none (resident step of each rank; the gather is timed by the default config)"},
+                    "sweep": rows, "clocks": sampler.summary(), "gpu_launches": int(launches), "impl": "b200"}
+            _REAL_STDOUT.write(json.dumps(line) + "\n")
+            _REAL_STDOUT.flush()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- one size: the headline (obs4096) or a single-path config ----------------------------------------------
+    wl = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=args.falloff)
+    task = wl.task
+    gather = igdist.ObsGather(task.obs_packed, total_envs=total, transport=args.gather) if world > 1 else None
+    pending = [None]
+
+    def obs_step(i):
+        if gather is not None:
+            gather.protect_source()        # last step's transfer has read obs_packed
+        wl.step()
+        if gather is not None:
+            t = gather.gather(task.obs_packed)
+            if args.sync_gather:
+                gather.wait(t)
+            pending[0] = t
+
+    def finish():
+        if gather is not None and pending[0] is not None:
+            gather.wait(pending[0])
+            pending[0] = None
+
     for i in range(W):
         obs_step(i)
+    finish()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = lib.igi_launch_count()
-    ms = timed(obs_step, args.steps, 0)
+    ms = timed(obs_step, args.steps, 0, after=finish)
     launches = int(lib.igi_launch_count() - launches0)   # kernels of libigi_b200.so inside the timed region
     sampler.stop_flag = True
-    task.tactile_engine.check_overflow()
+    if tactile:
+        task.tactile_engine.check_overflow()
     value = total * args.steps / (ms * 1e-3)
+    comm = None
+    if gather is not None:
+        comm = {"transport": args.gather, "bytes_per_rank_per_step": gather.bytes_per_step,
+                "bytes_into_learner_per_step": gather.bytes_per_step * (world - 1),
+                "bytes_received_per_rank_per_step": gather.bytes_per_step * (world - 1) if args.gather == "nccl" else 0,
+                "learner_wait_ms_last_step": gather.last_comm_ms(),
+                "overlap": "none (sync)" if args.sync_gather else "transfer of step i under the kernels of step i+1",
+                "sm_use": "none: copy-engine peer copies + stream memory ops" if args.gather == "p2p" else "NCCL all-gather kernels"}
+
+    # ---- the same resident leg under the other light model (single GPU): the two exact early-outs of tac_contact
+    # only fire when fragments clip, so the default number is reported next to the one that cannot use them
+    extra = {}
+    if tactile and world == 1 and not args.no_alt_falloff:
+        other = "none" if (args.falloff or "inverse_square") == "inverse_square" else "inverse_square"
+        wl2 = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=other, pin=False)
+        ms2 = timed(lambda i: wl2.step(), args.steps, W) / args.steps
+        t2 = timed(lambda i: wl2.task.update_tactile(wl2.ones, wl2.ones), max(args.steps // 2, 5), 3) / max(args.steps // 2, 5)
+        extra["alt_falloff"] = {"falloff": other, "ms_per_step": ms2, "value": total / (ms2 * 1e-3), "unit": UNIT,
+                                "tactile_pipeline_ms": t2,
+                                "tactile_roofline_frac": TACTILE_BYTES_PER_FRAME * 3 * E / (t2 * 1e-3) / 1e9 / _peak()[0]}
+        del wl2
+        torch.cuda.empty_cache()
 
     # ---- component timings + roofline (rank 0's GPU, same buffers, CUDA events) -----------------
-    extra = {}
-    if True:
+    if not args.no_components:
         K = max(args.steps // 2, 5)
-        eng = task.tactile_engine
-        fp = torch.stack((task.left_finger_pos, task.right_finger_pos, task.middle_finger_pos), 1).contiguous()
-        fq = torch.stack((task.left_finger_quat, task.right_finger_quat, task.middle_finger_quat), 1).contiguous()
-
-        def stage(mask):
-            return lambda i: eng.render(fp, fq, task.plug_pos, task.plug_quat, obs_out=task.tactile_imgs,
-                                        stage_mask=mask)
-        w_save, world_save = world, world
-        t_tac = timed(lambda i: task.update_tactile(ones, ones), K, 3) / K
-        t_geom = timed(stage(1), K, 3) / K
-        t_geomfill = timed(stage(8), K, 3) / K
-        t_fill = timed(stage(2), K, 3) / K
-        t_contact = timed(stage(4), K, 3) / K
-
-        def pcl_only(i):
-            task.invalidate_socket_cache()
-            task.update_external_cam(ones, ones, ones, zeros, zeros)
-        t_pcl = timed(pcl_only, K, 3) / K
-        gen = task.pcl_generator.engine
-        from isaacgyminsertion_b200.pcl_utils import filter_pts
-        t_compact = timed(lambda i: gen.compact(d_depth, d_seg, (2, 3), filter_pts.box), K, 3) / K
-        pts, cnt, any_ = gen.compact(d_depth, d_seg, (2, 3), filter_pts.box)
-        t_fps = timed(lambda i: gen.sample_fps(pts, cnt, any_, 0, 400, out=task._plug_pts), K, 3) / K
-        t_fps_both = timed(lambda i: gen.sample_fps(pts, cnt, any_, None, 400, out=task._both_pts), K, 3) / K
         frames = 3 * E
-        counts = eng.contact_counts()
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        peak, peak_src = _peak()
 
         def gbs(nbytes, t_ms):
             return nbytes / (t_ms * 1e-3) / 1e9
-        kernels = {
-            "tac_fill": {"ms": t_fill, "bytes": FILL_BYTES_PER_FRAME * frames},
-            "tac_geom": {"ms": t_geom, "bytes": None},
-            "tac_geom_fused_fill": {"ms": t_geomfill, "bytes": FILL_BYTES_PER_FRAME * frames},
-            "tac_contact": {"ms": t_contact, "bytes": None},
-            "tactile_pipeline": {"ms": t_tac, "bytes": TACTILE_BYTES_PER_FRAME * frames},
-            "pcl_compact": {"ms": t_compact, "bytes": (20736 * 2 + 128 + 96 * 4 + 54 * 4) * E},
-            "pcl_fps_plug": {"ms": t_fps, "bytes": None},
-            "pcl_fps_plug_socket": {"ms": t_fps_both, "bytes": None},
-            "pcl_pipeline": {"ms": t_pcl, "bytes": (PCL_BYTES_PER_ENV_FPS if args.sampler == "fps"
-                                                    else PCL_BYTES_PER_ENV_REF) * E},
-        }
+        kernels = {}
+        ones, zeros = wl.ones, wl.zeros
+        if tactile:
+            eng = task.tactile_engine
+            fp = (task.left_finger_pos, task.right_finger_pos, task.middle_finger_pos)
+            fq = (task.left_finger_quat, task.right_finger_quat, task.middle_finger_quat)
+
+            def stage(mask):
+                return lambda i: eng.render(fp, fq, task.plug_pos, task.plug_quat, obs_out=task.tactile_imgs,
+                                            stage_mask=mask)
+            t_tac = timed(lambda i: task.update_tactile(ones, ones), K, 3) / K
+            t_geom = timed(stage(1), K, 3) / K
+            t_geomfill = timed(stage(8), K, 3) / K
+            t_fill = timed(stage(2), K, 3) / K
+            t_contact = timed(stage(4), K, 3) / K
+            kernels.update({
+                "tac_fill": {"ms": t_fill, "bytes": FILL_BYTES_PER_FRAME * frames},
+                "tac_geom": {"ms": t_geom, "bytes": None},
+                "tac_geom_fused_fill": {"ms": t_geomfill, "bytes": FILL_BYTES_PER_FRAME * frames},
+                "tac_contact": {"ms": t_contact, "bytes": None},
+                "tactile_pipeline": {"ms": t_tac, "bytes": TACTILE_BYTES_PER_FRAME * frames}})
+        if pcl:
+            def pcl_only(i):
+                task.invalidate_socket_cache()
+                task.update_external_cam(ones, ones, ones, zeros, zeros)
+            t_pcl = timed(pcl_only, K, 3) / K
+            gen = task.pcl_generator.engine
+            from isaacgyminsertion_b200.pcl_utils import filter_pts
+            d_depth, d_seg = wl.d["depth"], wl.d["seg"]
+            t_compact = timed(lambda i: gen.compact(d_depth, d_seg, (2, 3), filter_pts.box), K, 3) / K
+            pts, cnt, any_ = gen.compact(d_depth, d_seg, (2, 3), filter_pts.box)
+            t_fps = timed(lambda i: gen.sample_fps(pts, cnt, any_, 0, 400, out=task._plug_pts), K, 3) / K
+            t_fps_both = timed(lambda i: gen.sample_fps(pts, cnt, any_, None, 400, out=task._both_pts), K, 3) / K
+            kernels.update({
+                "pcl_compact": {"ms": t_compact, "bytes": (20736 * 2 + 128 + 96 * 4 + 54 * 4) * E},
+                "pcl_fps_plug": {"ms": t_fps, "bytes": None},
+                "pcl_fps_plug_socket": {"ms": t_fps_both, "bytes": None},
+                "pcl_pipeline": {"ms": t_pcl, "bytes": (PCL_BYTES_PER_ENV_FPS if args.sampler == "fps"
+                                                        else PCL_BYTES_PER_ENV_REF) * E}})
         for k, v in kernels.items():
             if v["bytes"]:
                 v["gbs"] = gbs(v["bytes"], v["ms"])
                 v["frac"] = v["gbs"] / peak
-        # Dominant work = the tactile path.  Its two launches per step (tac_geom with the fused no-contact
-        # fill, then tac_contact over the frames with surviving triangles) share ONE algorithmic byte budget
-        # per frame (861 312 B), so they are reported together: achieved = frames x 861 312 B /
-        # (t_geom_fill + t_contact), both measured alone with CUDA events on the launching stream.  Charging
-        # the whole budget to either launch alone would overstate it.
-        t_dom = t_geomfill + t_contact
-        dom_bytes = TACTILE_BYTES_PER_FRAME * frames
-        ach = gbs(dom_bytes, t_dom)
-        # measured DRAM traffic of those launches (ncu --set full capture of this command, profiles/)
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if tr.get("envs_per_gpu") == E:
-                ks = tr["kernels"]
-                traffic = sum(ks[k]["dram_bytes_read"] + ks[k]["dram_bytes_write"] for k in ("tac_geom_fused_fill", "tac_contact"))
-        except Exception:
-            pass
-        extra["roofline"] = {"bound": "hbm", "kernel": "tac_geom(+fill) + tac_contact = the tactile path, 2 launches/step",
-                             "achieved": ach, "peak": peak, "unit": "GB/s",
-                             "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": t_dom,
-                             "share_of_step": t_dom / (ms / args.steps),
-                             "hbm_floor_ms": FILL_BYTES_PER_FRAME * frames / (peak * 1e9) * 1e3,
-                             "note": "mandatory DRAM traffic is the 359 424 B/frame of outputs (static sources are L2-resident); "
-                                     "tac_contact is issue-bound (rasterise + shade), not DRAM-bound",
-                             "pipeline": {"tactile": {"ms": t_tac, "GBps": kernels["tactile_pipeline"]["gbs"],
-                                                      "frac": kernels["tactile_pipeline"]["frac"]},
-                                          "pcl": {"ms": t_pcl, "GBps": kernels["pcl_pipeline"]["gbs"],
-                                                  "frac": kernels["pcl_pipeline"]["frac"]}}}
+        if tactile:
+            # Dominant work = the tactile path.  Its two launches per step (tac_geom with the fused no-contact
+            # fill, then tac_contact over the frames with surviving triangles) share ONE algorithmic byte budget
+            # per frame (861 312 B), so they are reported together: achieved = frames x 861 312 B /
+            # (t_geom_fill + t_contact), both measured alone with CUDA events on the launching stream.  Charging
+            # the whole budget to either launch alone would overstate it.
+            t_dom = t_geomfill + t_contact
+            dom_bytes = TACTILE_BYTES_PER_FRAME * frames
+            ach = gbs(dom_bytes, t_dom)
+            traffic = None     # measured DRAM traffic of those launches (ncu --set full capture of this command, profiles/)
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                if tr.get("envs_per_gpu") == E:
+                    ks = tr["kernels"]
+                    traffic = sum(ks[k]["dram_bytes_read"] + ks[k]["dram_bytes_write"] for k in ("tac_geom_fused_fill", "tac_contact"))
+            except Exception:
+                pass
+            counts = eng.contact_counts()
+            extra["roofline"] = {"bound": "hbm", "kernel": "tac_geom(+fill) + tac_contact = the tactile path, 2 launches/step",
+                                 "achieved": ach, "peak": peak, "unit": "GB/s",
+                                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": t_dom,
+                                 "share_of_step": t_dom / (ms / args.steps),
+                                 "hbm_floor_ms": FILL_BYTES_PER_FRAME * frames / (peak * 1e9) * 1e3,
+                                 "note": "mandatory DRAM traffic is the 359 424 B/frame of outputs (static sources are L2-resident); "
+                                         "tac_contact is issue-bound (rasterise + shade), not DRAM-bound",
+                                 "pipeline": {"tactile": {"ms": t_tac, "GBps": kernels["tactile_pipeline"]["gbs"],
+                                                          "frac": kernels["tactile_pipeline"]["frac"]}}}
+            extra["contact"] = {"frames": frames, "frames_with_candidates": int((counts > 0).sum().item()),
+                                "mean_candidate_tris": float(counts.clamp(min=0).float().mean().item()),
+                                "max_candidate_tris": int(counts.max().item()), "kmax": eng.kmax}
+            extra["tactile_frames_per_s"] = frames / (t_tac * 1e-3) * world
+        if pcl:
+            pr = {"ms": t_pcl, "GBps": kernels["pcl_pipeline"]["gbs"], "frac": kernels["pcl_pipeline"]["frac"]}
+            if tactile:
+                extra["roofline"]["pipeline"]["pcl"] = pr
+            else:
+                extra["roofline"] = {"bound": "hbm", "kernel": "pcl_compact + FPS = the point-cloud path", "achieved": pr["GBps"],
+                                     "peak": peak, "unit": "GB/s", "frac": pr["frac"], "traffic": None, "peak_source": peak_src,
+                                     "algorithmic_bytes_per_launch": kernels["pcl_pipeline"]["bytes"], "ms_per_launch": t_pcl,
+                                     "note": "FPS is a chain of dependent picks (latency / issue bound), not DRAM-bound"}
+            extra["pcl_obs_per_s"] = E / (t_pcl * 1e-3) * world
         extra["kernels"] = kernels
-        extra["contact"] = {"frames": frames, "frames_with_candidates": int((counts > 0).sum().item()),
-                            "mean_candidate_tris": float(counts.clamp(min=0).float().mean().item()),
-                            "max_candidate_tris": int(counts.max().item())}
-        extra["tactile_frames_per_s"] = frames / (t_tac * 1e-3) * world
-        extra["pcl_obs_per_s"] = E / (t_pcl * 1e-3) * world
 
     # ---- end to end: host buffers in, host result out, every step ------------------------------
     e2e = None
     if not args.no_e2e:
-        copy_bytes_in = sum(t.numel() * t.element_size() for t in (h_fpos, h_fquat, h_ppos, h_pquat, h_depth, h_seg))
-        copy_bytes_out = h_out.numel() * h_out.element_size()
-
         from isaacgyminsertion_b200.pipeline import HostObsPipeline
         from isaacgyminsertion_b200 import pipeline as _pl
         E2E_DEPTH = _pl.SLOTS - 1
         pipe = HostObsPipeline(task, sampler_socket_every_step=True)
-        copy_bytes_in, copy_bytes_out = pipe.h2d_bytes, pipe.d2h_bytes
         handles = []
+        h = wl.h
 
         def e2e_step(i):
             # host buffers in, host result out, every step: upload / kernels / download of
             # neighbouring steps overlap on three streams (isaacgyminsertion_b200.pipeline)
-            handles.append(pipe.step(h_fpos, h_fquat, h_ppos, h_pquat, h_depth, h_seg))
+            if gather is not None:
+                gather.protect_source()
+            handles.append(pipe.step(h["fpos"], h["fquat"], h["ppos"], h["pquat"], h["depth"], h["seg"]))
             if len(handles) > E2E_DEPTH:
                 handles.pop(0).wait()      # the learner reads the observations of step i - (SLOTS - 1)
-            if world > 1:
-                obs_gather(i)
+            if gather is not None:
+                pending[0] = gather.gather(task.obs_packed)
         # the same K steps as the resident leg; the timed region includes filling and draining the 3-stage
         # pipeline (first upload before any kernel, last download after the last kernel: ~5.6 ms at 4096 envs)
         K = max(args.steps, 5)
@@ -476,32 +580,40 @@ def main():
         def e2e_finish():
             while handles:
                 handles.pop(0).wait()
+            finish()
         ms_e2e = timed(e2e_step, K, 3, after=e2e_finish)
-        e2e = {"value": total * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": copy_bytes_in,
-               "d2h_bytes_per_step": copy_bytes_out, "ms_per_step": ms_e2e / K, "steps": K,
-               "overlap": "upload / kernels / download of neighbouring steps on 3 streams, 3-slot ring"}
-        load_state(d_fpos, d_fquat, h_ppos.to(dev), h_pquat.to(dev), d_depth, d_seg)
+        e2e = {"value": total * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
+               "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K, "steps": K,
+               "overlap": "upload / kernels / download of neighbouring steps on 3 streams, 3-slot ring",
+               "numa": numa}
+        wl.load_state()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_serial(gym, P, depth_np, seg_np, args.cpu_sample_envs)
+        cpu = cpu_baseline_serial(wl.gym, wl.P, wl.depth_np, wl.seg_np, args.cpu_sample_envs)
 
+    if gather is not None:
+        gather.close()
     if rank == 0:
+        what = ("3 allsight 224x224 tactile frames" if tactile else "") + (" + " if tactile and pcl else "") + \
+               ("96x54 depth+seg -> 400+400-pt cloud" if pcl else "")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"FactoryTaskInsertionTactile visuotactile obs: {E} envs/GPU x (3 allsight "
-                                   f"224x224 tactile frames + 96x54 depth+seg -> 400+400-pt cloud), "
+            "config": {"workload": f"FactoryTaskInsertionTactile visuotactile obs ({cfg}): {E} envs/GPU x ({what}), "
                                    f"sampler={args.sampler}, socket cloud recomputed every step",
-                       "envs_per_gpu": E, "total_envs": total, "sensors_per_env": 3, "sampler": args.sampler,
-                       "l2": "per-step outputs (4.4 GB) and depth/seg inputs (170 MB) exceed the 126 MB L2",
-                       "gather": ("none" if world == 1 else ("sync" if args.sync_gather else "overlapped"))},
+                       "config": cfg, "envs_per_gpu": E, "total_envs": total, "sensors_per_env": 3, "sampler": args.sampler,
+                       "falloff": args.falloff or "inverse_square (shipped yaml)",
+                       "l2": "per-step outputs (4.4 GB at 4096 envs) and depth/seg inputs (170 MB) exceed the 126 MB L2",
+                       "gather": ("none" if world == 1 else f"{args.gather}, " + ("sync" if args.sync_gather else "overlapped"))},
             "clocks": sampler.summary(),
             "gpu_launches": launches,
             "impl": "b200",
         }
         line.update(extra)
+        if comm:
+            line["comm"] = comm
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -511,6 +623,16 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    return (float(peaks.get("hbm_gbs", 6650.0)),
+            "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
 
 
 if __name__ == "__main__":

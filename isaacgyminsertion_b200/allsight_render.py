@@ -265,6 +265,7 @@ class BatchedAllSight:
         if on_overflow not in ("grow", "raise"):
             raise ValueError("on_overflow must be 'grow' or 'raise'")
         self.on_overflow = on_overflow
+        self.capturing = False      # True while a CUDA graph captures render(): no overflow telemetry inside the graph
         self.region_budget = 0      # test hook (IgiTactileFrames.region_budget)
         self.fill_split = 0         # tuning hook (IgiTactileFrames.fill_split)
         self.cfg = SensorConfig(sensor_yml, falloff=falloff)
@@ -402,6 +403,7 @@ class BatchedAllSight:
         update2: None or (N,) bool/uint8 masks, ANDed (update_freq & update_delay, task :523).
         Fills self.color / self.gel_depth / obs (default self.obs, shape (N,S,2048)); frames of
         envs whose update flag is off are left untouched."""
+        _poll = _poll and not self.capturing
         if _poll and stage_mask == 0:
             self.poll_overflow()
         obs = self.obs if obs_out is None else obs_out

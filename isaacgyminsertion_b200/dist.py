@@ -27,6 +27,59 @@ def init_from_env(backend=None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa(local_rank):
+    """Bind this process to the CPUs NVML reports as local to GPU `local_rank` and prefer that NUMA node for its
+    memory, BEFORE pinned host buffers are allocated (their pages are placed by the allocating thread's policy).
+    With 8 ranks on a two-socket host, unbound ranks stage half of their host<->device traffic through the other
+    socket.  Returns a small dict for the bench line (or {"error": ...}); never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = (int(vis.split(",")[local_rank]) if vis and all(v.strip().isdigit() for v in vis.split(","))
+               else local_rank)
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"bound": False, "why": "no overlap between the GPU-local CPUs and the allowed CPUs"}
+        os.sched_setaffinity(0, use)
+        node = None
+        base = "/sys/devices/system/node"
+        if os.path.isdir(base):
+            for name in sorted(os.listdir(base)):
+                if name.startswith("node") and name[4:].isdigit():
+                    try:
+                        txt = open(os.path.join(base, name, "cpulist")).read().strip()
+                    except OSError:
+                        continue
+                    members = set()
+                    for part in txt.split(","):
+                        if part:
+                            a, _, b = part.partition("-")
+                            members.update(range(int(a), int(b or a) + 1))
+                    if min(use) in members:
+                        node = int(name[4:])
+                        break
+        mem = False
+        if node is not None and node < 64:
+            try:     # set_mempolicy(MPOL_PREFERRED, {node}): x86_64 syscall 238, aarch64 237
+                import ctypes
+                import platform
+                nr = 238 if platform.machine() == "x86_64" else 237
+                m = ctypes.c_ulong(1 << node)
+                mem = ctypes.CDLL(None, use_errno=True).syscall(nr, 1, ctypes.byref(m), 65) == 0
+            except Exception:
+                mem = False
+        return {"bound": True, "gpu": idx, "cpus": len(use), "cpu_range": [min(use), max(use)], "node": node,
+                "mem_preferred": bool(mem)}
+    except Exception as e:      # no NVML, no permission: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 def env_slice(total_envs, rank, world):
     """Contiguous slice [lo, hi) of global env ids owned by `rank` (remainder to low ranks)."""
     base, rem = divmod(total_envs, world)

@@ -102,3 +102,61 @@ class HostObsPipeline:
         if self.i == 0:
             return None
         return self._last.wait()
+
+
+class GraphedObsStep:
+    """`compute_observations` of a task captured ONCE into a CUDA graph and replayed per step: at the env
+    counts the reference itself runs with these observations on (10 and 256, scripts/train_s3.sh:5,
+    train_s2.sh:5) a step is a dozen launches whose host cost exceeds their device time; the replay is one
+    launch.  Inputs are read from the tensors the task attributes point at when the graph is captured
+    (`left_finger_pos`, ..., `cam_renders`, `seg_renders`): write new values INTO them between replays.
+    Needs the FPS sampler (the reference sampler reads the host RNG every step) and update masks that live
+    in fixed tensors (default: all ones / no noise)."""
+
+    def __init__(self, task, masks=None, socket_every_step=False, warmup=3):
+        if task.pcl_cam and task.sampler != "fps":
+            raise RuntimeError("GraphedObsStep needs sampler='fps' (the reference sampler uploads host RNG words per step)")
+        self.task = task
+        dev = task.device
+        N = task.num_envs
+        ones = torch.ones(N, dtype=torch.bool, device=dev)
+        zeros = torch.zeros(N, dtype=torch.bool, device=dev)
+        self.masks = masks if masks is not None else (ones, ones, ones, ones, ones, zeros, zeros)
+        self.socket_every_step = socket_every_step
+        eng = task.tactile_engine if task.tactile else None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):       # first-use work (function attributes, scratch, side stream) outside the capture
+                self._body()
+            if eng is not None:
+                eng.check_overflow()
+                eng.capturing = True               # no host-visible telemetry inside the graph
+            try:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side):
+                    self._body()
+            finally:
+                if eng is not None:
+                    eng.capturing = False
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def _body(self):
+        t = self.task
+        if t.pcl_cam and self.socket_every_step:
+            t.invalidate_socket_cache()
+        t.compute_observations(*self.masks)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.task.obs_packed
+
+    def check_overflow(self):
+        """Triangle-list overflow of the replays so far (host sync; the graph itself carries no telemetry)."""
+        if self.task.tactile:
+            eng = self.task.tactile_engine
+            eng._ovf_host.copy_(eng._counters[2:4])
+            eng._ovf_event = torch.cuda.Event()
+            eng._ovf_event.record(torch.cuda.current_stream(eng.device))
+            return eng.check_overflow()
+        return False

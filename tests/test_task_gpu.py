@@ -210,6 +210,42 @@ def test_host_pipeline_matches_direct_calls(built_lib):
     assert torch.equal(pipe.flush(), want)
 
 
+def test_graphed_step_equals_eager_step(built_lib):
+    """The CUDA-graph replay of compute_observations (pipeline.GraphedObsStep) gives the eager step's rows bit for
+    bit, follows new input values written into the captured tensors, and keeps the update-mask semantics."""
+    from isaacgyminsertion_b200.pipeline import GraphedObsStep
+    n = 10                                 # the reference's visuotactile operating point (scripts/train_s3.sh:5)
+    gym, P, depth, seg = _inputs(n, seed=6)
+    task = _task(n, gym, P, sampler="fps", falloff="none")
+    _load(task, P, depth, seg)
+    ones = torch.ones(n, dtype=torch.bool, device=DEV)
+    zeros = torch.zeros(n, dtype=torch.bool, device=DEV)
+    task.invalidate_socket_cache()
+    task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
+    want = task.obs_packed.clone()
+    upd = ones.clone()
+    g = GraphedObsStep(task, masks=(upd, ones, upd, ones, ones, zeros, zeros), socket_every_step=True)
+    task.obs_packed.zero_()
+    assert torch.equal(g(), want)
+    # new poses / depth written INTO the captured input tensors
+    fp_all = task.left_finger_pos._base if task.left_finger_pos._base is not None else task.left_finger_pos
+    fp_all += 0.0015
+    task.cam_renders *= 1.01
+    task.invalidate_socket_cache()
+    task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
+    want2 = task.obs_packed.clone()
+    assert not torch.equal(want2, want)
+    task.obs_packed.zero_()
+    assert torch.equal(g(), want2)
+    # masks are read from the captured tensors too: envs switched off keep their rows
+    upd[::2] = False
+    fp_all -= 0.0015
+    g()
+    assert torch.equal(task.obs_packed[::2, :6144], want2[::2, :6144])          # tactile part untouched
+    assert torch.equal(task.obs_packed[1::2, :6144], want[1::2, :6144])
+    assert g.check_overflow() is False
+
+
 # --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_envs,falloff", [(1024, "inverse_square"), (4096, "inverse_square"), (4096, "none")])
 def test_full_size_tactile_properties(built_lib, n_envs, falloff):
