@@ -137,7 +137,10 @@ __device__ bool tri_bbox(const TacConst& kc, V3 A, V3 B, V3 C, int& x0, int& y0,
   return x0 <= x1 && y0 <= y1;
 }
 
-// Same box with reciprocal multiplies (geometry kernel: the +-1 pixel dilation absorbs the ulps).
+#ifndef BB_MARGIN
+#define BB_MARGIN 0.125f
+#endif
+// Tight box with reciprocal multiplies (geometry kernel).
 __device__ __forceinline__ bool tri_bbox_fast(const TacConst& kc, V3 A, V3 B, V3 C, int& x0, int& y0, int& x1, int& y1) {
   const float zn = kc.znear;
   const float zA = -A.z, zB = -B.z, zC = -C.z;
@@ -151,10 +154,16 @@ __device__ __forceinline__ bool tri_bbox_fast(const TacConst& kc, V3 A, V3 B, V3
   const float fx0 = (mnx - sx0) * kx, fx1 = (mxx - sx0) * kx;
   const float fy0 = (mxy - sy0) * ky, fy1 = (mny - sy0) * ky;
   if (fx1 < -2.0f || fy1 < -2.0f || fx0 > (float)(TW + 1) || fy0 > (float)(TH + 1)) return false;
-  x0 = (int)fmaxf(floorf(fx0) - 1.0f, 0.0f);
-  y0 = (int)fmaxf(floorf(fy0) - 1.0f, 0.0f);
-  x1 = (int)fminf(ceilf(fx1) + 1.0f, (float)(TW - 1));
-  y1 = (int)fminf(ceilf(fy1) + 1.0f, (float)(TH - 1));
+  // Pixel centres sit at integer coordinates here.  A centre can only be covered when it lies inside the
+  // projected triangle up to the rounding of cover()'s separately-rounded edge functions and of the fast
+  // reciprocals above (together < 0.01 pixel for the thin and short triangles of these meshes, see DESIGN.md
+  // "tight boxes"); BB_MARGIN = 1/8 pixel keeps the box conservative with an order of magnitude to spare.  Most
+  // mesh triangles are 1-3 pixels wide, so a box without the old +-1 pixel dilation has a third of the pixels,
+  // and triangles that fall between pixel centres are dropped here.
+  x0 = (int)fmaxf(ceilf(fx0 - BB_MARGIN), 0.0f);
+  y0 = (int)fmaxf(ceilf(fy0 - BB_MARGIN), 0.0f);
+  x1 = (int)fminf(floorf(fx1 + BB_MARGIN), (float)(TW - 1));
+  y1 = (int)fminf(floorf(fy1 + BB_MARGIN), (float)(TH - 1));
   return x0 <= x1 && y0 <= y1;
 }
 
