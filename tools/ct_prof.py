@@ -8,7 +8,9 @@ from isaacgyminsertion_b200 import _lib
 from isaacgyminsertion_b200.task_obs import FactoryTaskInsertionTactileObs
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 gym, P, depth, seg = bench.make_inputs(E, 0, E)
-task = FactoryTaskInsertionTactileObs(E, gym, P["mesh_id"], P["bg_id"], device="cuda:0", sampler="fps", strict_rng=False, pcl_cam=False)
+task = FactoryTaskInsertionTactileObs(E, gym, P["mesh_id"], P["bg_id"], device="cuda:0", sampler="fps", strict_rng=False, pcl_cam=False,
+                                      falloff=os.environ.get("IGI_FALLOFF") or None)
+print("falloff", task.tactile_engine.cfg.falloff)
 dev = task.device
 fp = torch.from_numpy(P["finger_pos"]).to(dev); fq = torch.from_numpy(P["finger_quat"]).to(dev)
 pp = torch.from_numpy(P["plug_pos"]).to(dev); pq = torch.from_numpy(P["plug_quat"]).to(dev)
