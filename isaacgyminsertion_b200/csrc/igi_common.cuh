@@ -93,5 +93,8 @@ __device__ __forceinline__ void igi_fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// fire-and-forget prefetch of the 128-byte line at p into L2
+__device__ __forceinline__ void igi_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ int igi_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int igi_warp() { return threadIdx.x >> 5; }

@@ -876,8 +876,14 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
   float* s_h = NCH == 1 ? s_diff + 1 : s_diff + (size_t)BUD * 3;
   __shared__ int s_off[CT_CHUNK];
   __shared__ int s_wsum[CT_BLOCK / 32];
-  __shared__ float sM[12];
-  __shared__ int s_frame, s_next, s_anydiff;
+  __shared__ int s_anydiff;
+  // Frame pipeline.  Frame ids come from the worklist TWO frames ahead, a frame's header (triangle count, dirty box,
+  // background id - written by tac_geom and long evicted from L2 by the 4 GB of fill traffic in between) ONE frame
+  // ahead: loaded into registers when a frame starts, parked in shared memory after its raster phase, and the next
+  // frame's setup / normal records are prefetched into L2 behind that.  No DRAM round trip stays on the critical
+  // path between two frames.
+  __shared__ int s_ring[3];     // frame ids: [it % 3] current, [(it + 1) % 3] next, [(it + 2) % 3] the one after
+  __shared__ int s_hdr[2][8];   // header of the frame of parity it & 1: K, box x0 y0 x1 y1, background id
   __shared__ int s_rctr, s_sctr;   // next raster item / next hit-box pixel to hand out
   __shared__ int s_hb[4];  // bounds of the frame's hit pixels (all sub-windows whose colour changed)
   __shared__ int s_sb[4];  // bounds of the hit pixels of the current sub-window's region
@@ -908,33 +914,51 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
     }
     igi_bulk_commit();
   };
-  // Work items are fetched ONE FRAME AHEAD: the zero fill of the next frame is issued when the current
-  // frame starts, so it has a whole frame time to land before that frame's first gel_depth write.
-  if (tid == 0) {
+  constexpr int HDR_N = 6;
+  auto fetch_id = [&]() {
     const int w = atomicAdd(a.cursor, 1);
-    s_next = (w < *a.work_n) ? a.worklist[w] : -1;
+    return (w < *a.work_n) ? a.worklist[w] : -1;
+  };
+  auto load_hdr = [&](int frame) -> int {   // thread tid < HDR_N loads word tid of the frame's header
+    if (frame < 0 || tid >= HDR_N) return 0;
+    if (tid == 0) return a.counts[frame];
+    if (tid < 5) return a.bbox[4 * frame + tid - 1];
+    return a.bg_id[frame];
+  };
+  if (tid == 0) {
+    s_ring[0] = fetch_id();
+    s_ring[1] = s_ring[0] >= 0 ? fetch_id() : -1;
   }
   __syncthreads();
-  zero_fill_async(s_next);
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      s_frame = s_next;
-      if (s_next >= 0) {
-        const int w = atomicAdd(a.cursor, 1);
-        s_next = (w < *a.work_n) ? a.worklist[w] : -1;
-      }
-      s_hb[0] = TW; s_hb[1] = TH; s_hb[2] = -1; s_hb[3] = -1;
-    }
-    __syncthreads();
-    const int f = s_frame;
+  {
+    const int v = load_hdr(s_ring[0]);
+    if (tid < HDR_N) s_hdr[0][tid] = v;
+  }
+  // The zero fill of a frame's gel_depth is issued when the frame BEFORE it starts, so it has a whole frame time to
+  // land before that frame's first gel_depth write.
+  zero_fill_async(s_ring[0]);
+  for (int it = 0;; ++it) {
+    __syncthreads();   // the previous frame is finished (its obs pixels read shared memory); ring and header slots are published
+    const int f = s_ring[it % 3];
     CT_T(0);
     if (f < 0) {
       igi_bulk_wait0();   // s_zero must outlive the copies that read it
       return;
     }
-    zero_fill_async(s_next);
-    const int K = a.counts[f];
+    zero_fill_async(s_ring[(it + 1) % 3]);
+    const int* hdr = s_hdr[it & 1];
+    const int K = hdr[0];
+    // Once per frame, at a point where a late warp 0 costs nothing (the raster batches are handed out dynamically):
+    // take the id of the frame after next from the worklist and bring the next frame's header into shared memory.
+    auto advance = [&]() {
+      if (tid < HDR_N) {
+        const int nf = s_ring[(it + 1) % 3];
+        const int v = load_hdr(nf);
+        if (tid == 0) s_ring[(it + 2) % 3] = nf >= 0 ? fetch_id() : -1;
+        s_hdr[(it + 1) & 1][tid] = v;
+      }
+    };
+    if (tid == 0) { s_hb[0] = TW; s_hb[1] = TH; s_hb[2] = -1; s_hb[3] = -1; }
     // Fused fill: the other parts of the frame's no-contact result that tac_geom left to this kernel go out
     // with plain stores while the raster / shading work of the frame runs; the barriers below order them
     // before the rewrite of the changed box.
@@ -943,14 +967,16 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
       fa.parts &= ~2;
       fill_frame(fa, f, tid, CT_BLOCK);
     }
-    if (K <= 0) continue;   // listed only to be filled
-    if (tid < 12) sM[tid] = a.M[(size_t)f * 12 + tid];
+    if (K <= 0) {   // listed only to be filled
+      advance();
+      continue;
+    }
     const Setup* list = a.setups + (size_t)f * a.kmax;
     const NRec* nlist = a.nrecs + (size_t)f * a.kmax;
     // window that can change: union of the triangle boxes, dilated by the blur radius
-    const int wx0 = max(a.bbox[4 * f + 0] - HALO, 0), wy0 = max(a.bbox[4 * f + 1] - HALO, 0);
-    const int wx1 = min(a.bbox[4 * f + 2] + HALO, TW - 1), wy1 = min(a.bbox[4 * f + 3] + HALO, TH - 1);
-    const uint8_t* bgr = a.bg_real + (size_t)a.bg_id[f] * TW * TH * 3;
+    const int wx0 = max(hdr[1] - HALO, 0), wy0 = max(hdr[2] - HALO, 0);
+    const int wx1 = min(hdr[3] + HALO, TW - 1), wy1 = min(hdr[4] + HALO, TH - 1);
+    const uint8_t* bgr = a.bg_real + (size_t)hdr[5] * TW * TH * 3;
     uint8_t* col = a.color + (size_t)f * TW * TH * 3;
     float* gdep = a.gel_depth + (size_t)f * TW * TH;
     // cut the window into the fewest sub-windows whose region (interior + halo) fits the budget
@@ -970,18 +996,6 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
         const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
         __syncthreads();
-        // --- z-buffer starts EMPTY (two pixels per 128-bit store, no index arithmetic, no global loads); the gel's
-        // depth is looked up per fragment instead (~5700 fragments per frame against ~8000 region pixels)
-        {
-          uint4* z4 = reinterpret_cast<uint4*>(s_z);
-          const int n4 = (RW * RH + 1) >> 1;
-          const uint32_t hi = (uint32_t)(CT_EMPTY >> 32);
-          for (int i = tid; i < n4; i += CT_BLOCK) z4[i] = make_uint4(0u, hi, 0u, hi);
-          if (NCH != 1) {   // three-channel path: the difference plane is separate from the keys
-            for (int i = tid; i < RW * RH * 3; i += CT_BLOCK) s_diff[i] = 0.0f;
-          }
-        }
-        if (tid == 0) { s_anydiff = 0; s_sctr = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
         CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
@@ -1000,6 +1014,19 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
               if (bx0 <= bx1 && by0 <= by1) rows[j] = by1 - by0 + 1;
             }
             sum += rows[j];
+          }
+          if (c0 == 0) {
+            // --- z-buffer starts EMPTY (two pixels per 128-bit store, no index arithmetic, no global loads; the gel's
+            // depth is looked up per fragment instead).  Placed here so that the stores run under the latency of the
+            // box loads above.
+            uint4* z4 = reinterpret_cast<uint4*>(s_z);
+            const int n4 = (RW * RH + 1) >> 1;
+            const uint32_t hi = (uint32_t)(CT_EMPTY >> 32);
+            for (int i = tid; i < n4; i += CT_BLOCK) z4[i] = make_uint4(0u, hi, 0u, hi);
+            if (NCH != 1) {   // three-channel path: the difference plane is separate from the keys
+              for (int i = tid; i < RW * RH * 3; i += CT_BLOCK) s_diff[i] = 0.0f;
+            }
+            if (tid == 0) { s_anydiff = 0; s_sctr = 0; s_sb[0] = TW; s_sb[1] = TH; s_sb[2] = -1; s_sb[3] = -1; }
           }
           int incl = sum;
 #pragma unroll
@@ -1026,6 +1053,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
           if (tid == 0) s_rctr = 0;
           __syncthreads();
           CT_T(2);
+          if (c0 == 0 && tx == wx0 && ty == wy0) advance();   // first chunk of the frame's first region
           if (tid == 0) { CT_COUNT(9, total); CT_COUNT(12, 1); CT_COUNT(13, RW * RH); CT_COUNT(14, kn); }
           for (;;) {
             int i0 = 0;
@@ -1114,6 +1142,16 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         igi_bulk_wait1();   // this frame's zero fill has landed; only the next frame's group may still be in flight
         __syncthreads();
         CT_T(3);
+        if (tx == wx0 && ty == wy0) {
+          // the next frame's triangle records (written by tac_geom, in DRAM by now) -> L2, one 128-byte line per thread
+          const int Kn = s_hdr[(it + 1) & 1][0], fn = s_ring[(it + 1) % 3];
+          if (fn >= 0 && Kn > 0) {
+            const char* p0 = reinterpret_cast<const char*>(a.setups + (size_t)fn * a.kmax);
+            const char* p1 = reinterpret_cast<const char*>(a.nrecs + (size_t)fn * a.kmax);
+            for (int o = tid * 128; o < Kn * (int)sizeof(Setup); o += CT_BLOCK * 128) igi_prefetch_l2(p0 + o);
+            for (int o = tid * 128; o < Kn * (int)sizeof(NRec); o += CT_BLOCK * 128) igi_prefetch_l2(p1 + o);
+          }
+        }
         if (s_sb[2] < 0) continue;  // nothing of the peg is visible here: fill already wrote the result
         // --- shade hits, build the scaled difference image (0 where the gel is visible).  Only the box of the hit
         // pixels is scanned; each warp takes 32 box pixels at a time, queues the hit ones and shades a full warp of
