@@ -80,6 +80,14 @@ def bind_to_gpu_numa(local_rank):
         return {"bound": False, "why": f"{type(e).__name__}: {e}"}
 
 
+def shard_word_window(nonempty_per_rank, rank, m):
+    """Reference sampler on sharded envs (pcl_utils.BatchedPointCloud.sample_reference): the reference draws m
+    `torch.randint` words per NON-EMPTY env in global env order, so rank `rank` starts `skip` words into the stream
+    and the whole job consumes `total` words.  -> (skip, total)."""
+    counts = [int(c) for c in nonempty_per_rank]
+    return m * sum(counts[:rank]), m * sum(counts)
+
+
 def env_slice(total_envs, rank, world):
     """Contiguous slice [lo, hi) of global env ids owned by `rank` (remainder to low ranks)."""
     base, rem = divmod(total_envs, world)
@@ -162,9 +170,15 @@ class ObsGather:
         self.comm_ms = None
         if self.transport == "none":
             return
-        if self.device.type == "cuda":
-            self.stream = torch.cuda.Stream(device=self.device)
-            self._ev_ready = torch.cuda.Event()
+        if self.device.type != "cuda":
+            # host tensors (gloo, the CPU tests): one synchronous collective per step, same slot rotation
+            if transport != "nccl":
+                raise RuntimeError("ObsGather on host tensors supports only the collective transport ('nccl')")
+            self.transport = "host"
+            self._out = [torch.empty((self.total, self.row), dtype=torch.float32) for _ in range(self.slots)]
+            return
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._ev_ready = torch.cuda.Event()
         if self.transport == "nccl":
             self._out = [torch.empty((self.total, self.row), dtype=torch.float32, device=self.device)
                          for _ in range(self.slots)]
@@ -237,6 +251,9 @@ class ObsGather:
             return obs
         self.step += 1
         s, slot = self.step, self.step % self.slots
+        if self.transport == "host":
+            out = gather_observations(obs, self.total, out=self._out[slot] if self.total % self.world == 0 else None)
+            return ("host", out, None)
         cur = torch.cuda.current_stream(self.device)
         if self.transport == "nccl":
             if self._work is not None:
@@ -315,6 +332,8 @@ class ObsGather:
         if self.transport == "none":
             return ticket
         kind, out, h = ticket
+        if kind == "host":
+            return out
         cur = torch.cuda.current_stream(self.device)
         if kind == "nccl" and not isinstance(h, torch.cuda.Event):
             h.wait()
@@ -339,6 +358,7 @@ class ObsGather:
         if self.transport == "nccl" and self._work is not None:
             self._work.wait()
         if self.transport != "p2p":
+            self.transport = "none"
             return
         torch.cuda.synchronize(self.device)
         dist.barrier()

@@ -224,9 +224,8 @@ class BatchedPointCloud:
             mine = (any_[:, cls] != 0).sum().to(torch.int64).reshape(1)
             every = torch.empty(dist.get_world_size(), dtype=torch.int64, device=self.device)
             dist.all_gather_into_tensor(every, mine)
-            every = every.cpu().tolist()
-            skip = m * int(sum(every[:dist.get_rank()]))
-            total_words = m * int(sum(every))
+            from .dist import shard_word_window
+            skip, total_words = shard_word_window(every.cpu().tolist(), dist.get_rank(), m)
         raw_np = self.rng_stream.peek(skip + n * m)[skip:]
         raw = torch.from_numpy(raw_np.view(np.int32).copy()).to(self.device, non_blocking=False)
         idx = torch.empty((n, m), dtype=torch.int32, device=self.device) if return_idx else None

@@ -61,6 +61,54 @@ def test_gather_observations_world2_gloo(total):
         assert shape == (total, row)
 
 
+def _worker_obsgather(rank, world, port, total, row, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    igdist.init_from_env(backend="gloo")
+    lo, hi = igdist.env_slice(total, rank, world)
+    ok = True
+    g = igdist.ObsGather(torch.zeros(hi - lo, row), total_envs=total, transport="nccl")
+    held = None
+    for step in range(1, 5):      # slot rotation: the result of step s stays intact until gather(s + 1) is called
+        local = torch.arange(lo, hi, dtype=torch.float32)[:, None] * 10 + step * 1000 + torch.arange(row, dtype=torch.float32)[None]
+        want = torch.arange(total, dtype=torch.float32)[:, None] * 10 + step * 1000 + torch.arange(row, dtype=torch.float32)[None]
+        got = g.wait(g.gather(local))
+        ok = ok and bool(torch.equal(got, want))
+        if held is not None:
+            ok = ok and bool(torch.equal(held[0], held[1]))      # the previous step's tensor was not overwritten
+        held = (got, want.clone())
+    g.close()
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 9])
+def test_obsgather_collective_transport_world2_gloo(total):
+    world, row = 2, 12
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_obsgather, args=(r, world, port, total, row, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_sharded_reference_sampler_word_windows():
+    """m words per non-empty env in GLOBAL env order: the ranks' windows tile the job's words without gap or overlap."""
+    m, counts = 400, [3, 0, 5, 2]
+    wins = [igdist.shard_word_window(counts, r, m) for r in range(len(counts))]
+    assert [w[0] for w in wins] == [0, 1200, 1200, 3200] and all(w[1] == 4000 for w in wins)
+    for r in range(len(counts) - 1):
+        assert wins[r][0] + m * counts[r] == wins[r + 1][0]
+    assert igdist.shard_word_window([7], 0, 400) == (0, 2800)
+
+
 def test_single_process_gather_is_identity():
     x = torch.randn(5, 7)
     assert igdist.gather_observations(x) is x
