@@ -229,8 +229,9 @@ __device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ft
 // channel.  Each light adds a non-negative term (n.l >= 0.001, attenuation >= 0, BRDF terms >= 0) and the output
 // clamps at 1.0 -> 255, so the result is bit-identical; it only skips work for fragments that clip (every
 // fragment under the inverse-square light model with the shipped intensities).
+// `voting` = false: this lane only keeps the warp converged (its result is discarded) and votes "clipped".
 template <int NCH, int NL, bool EARLY = false>
-__device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t* rgb) {
+__device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t* rgb, bool voting = true) {
   const float A2_PI = kc.sh_a2 * 0.31830988618379067f;
   const float ipl = fast_rsqrt(p.x * p.x + p.y * p.y + p.z * p.z);
   const V3 v{-p.x * ipl, -p.y * ipl, -p.z * ipl};
@@ -273,7 +274,7 @@ __device__ __forceinline__ void shade_t(const TacConst& kc, V3 p, V3 n, uint8_t*
     if (EARLY) {
       bool clipped = true;
 #pragma unroll
-      for (int k = 0; k < NCH; ++k) clipped = clipped && col[k] >= 1.0f;
+      for (int k = 0; k < NCH; ++k) clipped = clipped && (col[k] >= 1.0f || !voting);
       if (__all_sync(0xffffffffu, clipped)) break;
     }
   }
@@ -959,6 +960,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
       }
     };
     if (tid == 0) { s_hb[0] = TW; s_hb[1] = TH; s_hb[2] = -1; s_hb[3] = -1; }
+    bool frame_changed = false;
     // Fused fill: the other parts of the frame's no-contact result that tac_geom left to this kernel go out
     // with plain stores while the raster / shading work of the frame runs; the barriers below order them
     // before the rewrite of the changed box.
@@ -995,7 +997,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         const int rx0 = tx - HALO, ry0 = ty - HALO;
         const int cx0 = max(rx0, 0), cy0 = max(ry0, 0);
         const int cx1 = min(ix1 + HALO, TW - 1), cy1 = min(iy1 + HALO, TH - 1);
-        __syncthreads();
+        if (tx != wx0 || ty != wy0) __syncthreads();   // (the frame's first region starts behind the barrier at the top of the frame loop)
         CT_T(1);
         // --- raster: work items are (triangle, image row) pairs, enumerated with a block scan so that
         // every thread gets the same number of rows whatever the triangle sizes are
@@ -1034,7 +1036,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
             const int t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
           }
-          __syncthreads();  // previous chunk's readers of s_off / s_wsum are done; z init visible
+          if (c0 > 0) __syncthreads();  // the previous chunk's readers of s_off / s_wsum are done (chunk 0 starts behind a barrier anyway)
           if (lane == 31) s_wsum[warp] = incl;
           __syncthreads();
           int woff = 0, total = 0;
@@ -1166,33 +1168,37 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
           bool nz_any = false;
           // all 32 lanes run the arithmetic (warp-uniform early-out votes inside shade_t); `act` gates the writes
           auto shade_px = [&](int i, bool act) {
-            const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
-            const int px = rx0 + rx, py = ry0 + ry;
-            const unsigned long long key = s_z[i];
-            const uint32_t low = (uint32_t)key;
-            const float t = __uint_as_float((uint32_t)(key >> 32));
-            const int slot = (int)((low - 1u) & 0xfffu);
-            const Setup s = load_setup(list + slot);
-            const uint4* nq = reinterpret_cast<const uint4*>(nlist + slot);
-            const uint4 na = __ldg(nq), nb = __ldg(nq + 1), nc = __ldg(nq + 2);
-            const float dx = s_dxp[px], dy = s_dyp[py];
-            const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
-            const float es = add(add(e0, e1), e2);
-            const float ies = __fdividef(1.0f, es);
-            const float l1 = e1 * ies, l2 = e2 * ies;
-            const float l0 = 1.0f - l1 - l2;
-            // barycentric blend of the camera-frame vertex normals (rotation and blend commute)
-            V3 n;
-            n.x = l0 * __uint_as_float(na.x) + l1 * __uint_as_float(na.w) + l2 * __uint_as_float(nb.z);
-            n.y = l0 * __uint_as_float(na.y) + l1 * __uint_as_float(nb.x) + l2 * __uint_as_float(nb.w);
-            n.z = l0 * __uint_as_float(na.z) + l1 * __uint_as_float(nb.y) + l2 * __uint_as_float(nc.x);
-            {
+            // lanes without a pixel (the last, partial batch of a warp) run the shader on a dummy fragment: they
+            // touch no shared memory, so no lane reads a key that another lane of the warp is about to overwrite
+            V3 pp{0.f, 0.f, -1.f}, n{0.f, 0.f, 1.f};
+            float t = 1.0f;
+            int px = 0, py = 0;
+            if (act) {
+              const int ry = (int)__umulhi((uint32_t)i, inv_rw), rx = i - ry * RW;
+              px = rx0 + rx; py = ry0 + ry;
+              const unsigned long long key = s_z[i];
+              const uint32_t low = (uint32_t)key;
+              t = __uint_as_float((uint32_t)(key >> 32));
+              const int slot = (int)((low - 1u) & 0xfffu);
+              const Setup s = load_setup(list + slot);
+              const uint4* nq = reinterpret_cast<const uint4*>(nlist + slot);
+              const uint4 na = __ldg(nq), nb = __ldg(nq + 1), nc = __ldg(nq + 2);
+              const float dx = s_dxp[px], dy = s_dyp[py];
+              const float e0 = edge_fn(dx, dy, s.n0), e1 = edge_fn(dx, dy, s.n1), e2 = edge_fn(dx, dy, s.n2);
+              const float es = add(add(e0, e1), e2);
+              const float ies = __fdividef(1.0f, es);
+              const float l1 = e1 * ies, l2 = e2 * ies;
+              const float l0 = 1.0f - l1 - l2;
+              // barycentric blend of the camera-frame vertex normals (rotation and blend commute)
+              n.x = l0 * __uint_as_float(na.x) + l1 * __uint_as_float(na.w) + l2 * __uint_as_float(nb.z);
+              n.y = l0 * __uint_as_float(na.y) + l1 * __uint_as_float(nb.x) + l2 * __uint_as_float(nb.w);
+              n.z = l0 * __uint_as_float(na.z) + l1 * __uint_as_float(nb.y) + l2 * __uint_as_float(nc.x);
               const float r = rsqrtf(fmaxf(n.x * n.x + n.y * n.y + n.z * n.z, 1e-30f));
               n.x *= r; n.y *= r; n.z *= r;
+              pp = V3{mul(dx, t), mul(dy, t), -t};
             }
-            V3 pp{mul(dx, t), mul(dy, t), -t};
             uint8_t rgb[3];
-            shade_t<NCH, 0, CT_EARLY_OUT != 0>(kc, pp, n, rgb);
+            shade_t<NCH, 0, CT_EARLY_OUT != 0>(kc, pp, n, rgb, act);
             if (!act) return;
             const uint8_t* bs = a.bg_sim + (py * TW + px) * 3;
             // gel_depth = depth0 - depth (allsight_render.py:193-197), interior pixels only
@@ -1230,7 +1236,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
               shade_px(idx, true);
             }
           }
-          if (qn > 0) shade_px(q[lane < qn ? lane : 0], lane < qn);
+          if (qn > 0) shade_px(lane < qn ? q[lane] : 0, lane < qn);
           if (__any_sync(0xffffffffu, nz_any) && lane == 0) s_anydiff = 1;
         }
         __syncthreads();
@@ -1241,6 +1247,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         // fill already wrote and the observation is the empty one.  Exact, not an approximation.
         if (!s_anydiff) continue;
 #endif
+        frame_changed = true;   // uniform: every thread read the same flag behind the same barrier
         // Only pixels within the blur radius of a hit can differ from what tac_fill wrote (the difference
         // image is 0 elsewhere): the changed box = hit box dilated by HALO, inside the interior.
         const int bx0 = max(hbx0 - HALO, tx), bx1 = min(hbx1 + HALO, ix1);
@@ -1337,6 +1344,7 @@ __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(
         }
         CT_T(6);
       }
+    if (!frame_changed) continue;   // no region changed a colour: the obs row stays the empty one the fill wrote
     __syncthreads();
     CT_T(7);
     // --- obs pixels whose 3.5x3.5 source window meets a pixel that changed ---------------------
