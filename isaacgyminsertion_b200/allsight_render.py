@@ -12,6 +12,7 @@ No CPU fallback: the device must be CUDA and libigi_b200.so must be built.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -267,7 +268,7 @@ class BatchedAllSight:
         self.on_overflow = on_overflow
         self.capturing = False      # True while a CUDA graph captures render(): no overflow telemetry inside the graph
         self.region_budget = 0      # test hook (IgiTactileFrames.region_budget)
-        self.fill_split = 0         # tuning hook (IgiTactileFrames.fill_split)
+        self.fill_split = int(os.environ.get("IGI_FILL_SPLIT", "0"))   # tuning hook (IgiTactileFrames.fill_split)
         self.cfg = SensorConfig(sensor_yml, falloff=falloff)
         packed = _assets.load_packed(assets_path)
         if meshes is None:
