@@ -862,8 +862,13 @@ __device__ __forceinline__ void raster_frag_depth(float znear, V3 N, float det, 
   z_test(t, d0, orig, k, zp, hb, px, py);
 }
 
+#ifdef CT_MAXNREG   // experiment hook: cap the registers instead of asking for CT_CTAS resident CTAs
+template <int NCH>
+__global__ void __maxnreg__(CT_MAXNREG) tac_contact(const __grid_constant__ TacConst kc, ContactArgs a) {
+#else
 template <int NCH>
 __global__ void __launch_bounds__(CT_BLOCK, NCH == 1 ? CT_CTAS : 1) tac_contact(const __grid_constant__ TacConst kc, ContactArgs a) {
+#endif
 #ifdef CT_PROFILE
   long long t_prof = clock64();
 #endif
