@@ -405,7 +405,16 @@ def main():
     # ---- one size: the headline (obs4096) or a single-path config ----------------------------------------------
     wl = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=args.falloff)
     task = wl.task
-    gather = igdist.ObsGather(task.obs_packed, total_envs=total, transport=args.gather) if world > 1 else None
+    gather, gather_note = None, None
+    if world > 1:
+        try:
+            gather = igdist.ObsGather(task.obs_packed, total_envs=total, transport=args.gather)
+        except RuntimeError as e:      # raised on every rank alike (dist.ObsGather._init_p2p): fall back together
+            if args.gather != "p2p":
+                raise
+            gather_note = f"p2p transport unavailable on this box, NCCL all-gather used instead: {e}"[:400]
+            args.gather = "nccl"
+            gather = igdist.ObsGather(task.obs_packed, total_envs=total, transport="nccl")
     pending = [None]
 
     def obs_step(i):
@@ -443,6 +452,8 @@ def main():
                 "learner_wait_ms_last_step": gather.last_comm_ms(),
                 "overlap": "none (sync)" if args.sync_gather else "transfer of step i under the kernels of step i+1",
                 "sm_use": "none: copy-engine peer copies + stream memory ops" if args.gather == "p2p" else "NCCL all-gather kernels"}
+        if gather_note:
+            comm["note"] = gather_note
 
     # ---- the same resident leg under the other light model (single GPU): the two exact early-outs of tac_contact
     # only fire when fragments clip, so the default number is reported next to the one that cannot use them

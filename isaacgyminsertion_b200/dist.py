@@ -192,6 +192,9 @@ class ObsGather:
 
     # ---- p2p setup --------------------------------------------------------------------------------
     def _init_p2p(self):
+        """Collective.  Either every rank ends up with the learner's block mapped and working stream memory
+        operations, or EVERY rank raises RuntimeError (so a caller can fall back to the NCCL transport on all ranks
+        at once): each step that can fail locally is followed by an exchange of the outcome."""
         from . import _lib
         self.lib = lib = _lib.load()
         self._check = _lib.check
@@ -202,40 +205,59 @@ class ObsGather:
         my_bytes = (self.slots * slot_bytes + 256 * self.world) if is_learner else 0
         my_bytes += 1024
         ptr, handle = c.c_void_p(), (c.c_ubyte * 64)()
-        with torch.cuda.device(self.device):
-            self._check(lib.igi_peer_alloc(c.c_ulonglong(my_bytes), c.byref(ptr), handle), "igi_peer_alloc")
-        self._own = ptr.value
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle))
-        # control words at the END of every rank's block: [consumed | staging_a | staging_b]
+        err = None
+        self._own, self._mapped = None, {}
+        try:
+            with torch.cuda.device(self.device):
+                self._check(lib.igi_peer_alloc(c.c_ulonglong(my_bytes), c.byref(ptr), handle), "igi_peer_alloc")
+                self._own = ptr.value
+                # stream memory operations must work on this device (probe on a spare word of the own block)
+                probe = self._own + my_bytes - 1024 + 16
+                st = c.c_void_p(self.stream.cuda_stream)
+                self._check(lib.igi_stream_write_value32(st, c.c_void_p(probe), c.c_uint(1)), "igi_stream_write_value32")
+                self._check(lib.igi_stream_wait_value32_geq(st, c.c_void_p(probe), c.c_uint(1)), "igi_stream_wait_value32_geq")
+                self.stream.synchronize()
+        except RuntimeError as e:
+            err = str(e)
+        outcomes = [None] * self.world
+        dist.all_gather_object(outcomes, (bytes(handle), err))
+        self._raise_if_any(outcomes, "allocating the peer block / stream memory operations")
+        handles = [o[0] for o in outcomes]
+        # control words at the END of every rank's block: [consumed | staging_a | staging_b | probe]
         self._ctl = self._own + my_bytes - 1024
-        self._mapped = {}
-        if is_learner:
-            self._data = self._own
-            self._arrived = self._own + self.slots * slot_bytes
-            self._peer_ctl = {}
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
+        err = None
+        try:
+            if is_learner:
+                self._data = self._own
+                self._arrived = self._own + self.slots * slot_bytes
+                self._peer_ctl = {}
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    p = c.c_void_p()
+                    h = (c.c_ubyte * 64).from_buffer_copy(handles[r])
+                    with torch.cuda.device(self.device):
+                        self._check(lib.igi_peer_open(h, c.byref(p)), "igi_peer_open")
+                    self._mapped[r] = p.value
+                    self._peer_ctl[r] = p.value            # a non-learner block is just its control words
+                self._slot_views = [_view(self._data + i * slot_bytes, slot_bytes, self.device, torch.float32,
+                                          (self.total, self.row)) for i in range(self.slots)]
+                self._ev_done = torch.cuda.Event()
+                self._ev_t0 = torch.cuda.Event(enable_timing=True)
+                self._ev_t1 = torch.cuda.Event(enable_timing=True)
+            else:
                 p = c.c_void_p()
-                h = (c.c_ubyte * 64).from_buffer_copy(handles[r])
+                h = (c.c_ubyte * 64).from_buffer_copy(handles[self.learner])
                 with torch.cuda.device(self.device):
                     self._check(lib.igi_peer_open(h, c.byref(p)), "igi_peer_open")
-                self._mapped[r] = p.value
-                self._peer_ctl[r] = p.value            # a non-learner block is just its control words
-            self._slot_views = [_view(self._data + i * slot_bytes, slot_bytes, self.device, torch.float32,
-                                      (self.total, self.row)) for i in range(self.slots)]
-            self._ev_done = torch.cuda.Event()
-            self._ev_t0 = torch.cuda.Event(enable_timing=True)
-            self._ev_t1 = torch.cuda.Event(enable_timing=True)
-        else:
-            p = c.c_void_p()
-            h = (c.c_ubyte * 64).from_buffer_copy(handles[self.learner])
-            with torch.cuda.device(self.device):
-                self._check(lib.igi_peer_open(h, c.byref(p)), "igi_peer_open")
-            self._mapped[self.learner] = p.value
-            self._data = p.value
-            self._arrived = p.value + self.slots * slot_bytes
+                self._mapped[self.learner] = p.value
+                self._data = p.value
+                self._arrived = p.value + self.slots * slot_bytes
+        except RuntimeError as e:
+            err = str(e)
+        outcomes = [None] * self.world
+        dist.all_gather_object(outcomes, (None, err))
+        self._raise_if_any(outcomes, "mapping the peer blocks over CUDA IPC")
         self._slot_bytes = slot_bytes
         # local snapshots of this rank's rows (two, alternating): the copy over NVLink reads the snapshot, so the next
         # step's kernels can rewrite the rows while the transfer is still in flight
@@ -243,6 +265,22 @@ class ObsGather:
         self._snap = None if is_learner else [torch.empty((self.rows, self.row), dtype=torch.float32, device=self.device)
                                               for _ in range(2)]
         dist.barrier()
+
+    def _raise_if_any(self, outcomes, what):
+        bad = [(r, o[1]) for r, o in enumerate(outcomes) if o[1]]
+        if not bad:
+            return
+        with torch.cuda.device(self.device):       # release what this rank holds, then fail on every rank alike
+            for p in self._mapped.values():
+                self.lib.igi_peer_close(ctypes.c_void_p(p))
+            self._mapped = {}
+            dist.barrier()
+            if self._own:
+                self.lib.igi_peer_free(ctypes.c_void_p(self._own))
+                self._own = None
+        self.transport = "none"
+        raise RuntimeError(f"ObsGather p2p transport unavailable ({what}): " +
+                           "; ".join(f"rank {r}: {m}" for r, m in bad))
 
     # ---- per step ---------------------------------------------------------------------------------
     @torch.no_grad()
