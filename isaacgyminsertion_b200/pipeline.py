@@ -46,6 +46,10 @@ class HostObsPipeline:
                         ppos=torch.empty((N, 3), dtype=f32, device=dev), pquat=torch.empty((N, 4), dtype=f32, device=dev),
                         depth=torch.empty((N, H, W), dtype=f32, device=dev), seg=torch.empty((N, H, W), dtype=i32, device=dev))
         self.d_in = [mk() for _ in range(SLOTS)]
+        # segmentation ids fit a byte (table 0, arm 1, plug 2, socket 3, factory_env_insertion.py:814-848): a host that
+        # keeps them as uint8 uploads a quarter of the bytes; they are widened on the device into the int32 image the
+        # task reads (the reference's camera tensor type)
+        self.d_seg8 = None
         self.d_out = [torch.empty_like(task.obs_packed) for _ in range(SLOTS)]
         self.h_out = [torch.empty(task.obs_packed.shape, dtype=f32).pin_memory() for _ in range(SLOTS)]
         self.ev_up = [torch.cuda.Event() for _ in range(SLOTS)]      # inputs of slot ready on the device
@@ -62,7 +66,9 @@ class HostObsPipeline:
     @torch.no_grad()
     def step(self, fpos, fquat, ppos, pquat, depth, seg, update=None):
         """Submit one step (host tensors, ideally pinned); never blocks the host.  Returns a
-        PendingObs for this step's observations."""
+        PendingObs for this step's observations.  `seg` may be int32 (the reference's tensor type) or uint8
+        (the ids are 0..3): the uint8 form uploads a quarter of the bytes and is widened on the device."""
+        self.last_h2d_bytes = sum(t.numel() * t.element_size() for t in (fpos, fquat, ppos, pquat, depth, seg))
         task, i = self.task, self.i
         slot = i % SLOTS
         cur = torch.cuda.current_stream(self.dev)
@@ -71,8 +77,15 @@ class HostObsPipeline:
             if i >= SLOTS:
                 self.s_up.wait_event(self.ev_done[slot])
             d = self.d_in[slot]
-            for k, src in (("fpos", fpos), ("fquat", fquat), ("ppos", ppos), ("pquat", pquat), ("depth", depth), ("seg", seg)):
+            for k, src in (("fpos", fpos), ("fquat", fquat), ("ppos", ppos), ("pquat", pquat), ("depth", depth)):
                 d[k].copy_(src.reshape(d[k].shape), non_blocking=True)
+            if seg.dtype == torch.uint8:
+                if self.d_seg8 is None:
+                    self.d_seg8 = [torch.empty(d["seg"].shape, dtype=torch.uint8, device=self.dev) for _ in range(SLOTS)]
+                self.d_seg8[slot].copy_(seg.reshape(d["seg"].shape), non_blocking=True)
+                d["seg"].copy_(self.d_seg8[slot])            # widen on the device (upload stream)
+            else:
+                d["seg"].copy_(seg.reshape(d["seg"].shape), non_blocking=True)
             self.ev_up[slot].record(self.s_up)
         # kernels
         cur.wait_event(self.ev_up[slot])
