@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--cpu-sample-envs", type=int, default=8)
     ap.add_argument("--no-overlap", action="store_true", help="point-cloud path on the same stream as the tactile path")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    ap.add_argument("--one-input-set", action="store_true",
+                    help="every timed step sees the same poses / camera frames (default: two seeded sets, alternating)")
     ap.add_argument("--seg-int32-host", action="store_true",
                     help="e2e leg: keep the host copy of the segmentation image as int32 (default: uint8, widened on the device)")
     return ap.parse_args()
@@ -264,7 +266,7 @@ def run_reference(args):
 class Workload:
     """One rank's task object + device-resident inputs + pinned host copies of them."""
 
-    def __init__(self, E, offset, total, dev, args, tactile=True, pcl=True, falloff=None, pin=True):
+    def __init__(self, E, offset, total, dev, args, tactile=True, pcl=True, falloff=None, pin=True, two_sets=False):
         import torch
         from isaacgyminsertion_b200.task_obs import FactoryTaskInsertionTactileObs
         self.E, self.dev = E, dev
@@ -285,12 +287,24 @@ class Workload:
             # host copy of the segmentation image as uint8 (ids 0..3): a quarter of the upload; widened on the device
             assert self.seg_np.min() >= 0 and self.seg_np.max() <= 255
             self.h["seg"] = host(self.seg_np.astype(np.uint8))
+        self.sets_h, self.sets_d = [self.h], [self.d]
+        if two_sets:
+            # a second set of poses and camera frames (seed 1; same meshes and backgrounds, they are static per env):
+            # the timed steps alternate between the two, so the contact mix under the work stealing is not frozen
+            _, P2, depth2, seg2 = make_inputs(E, offset, total, seed=1)
+            h2 = dict(fpos=host(P2["finger_pos"]), fquat=host(P2["finger_quat"]), ppos=host(P2["plug_pos"]),
+                      pquat=host(P2["plug_quat"]), depth=host(depth2), seg=host(seg2))
+            self.sets_d.append({k: v.to(dev) for k, v in h2.items()})
+            if not args.seg_int32_host:
+                h2["seg"] = host(seg2.astype(np.uint8))
+            self.sets_h.append(h2)
+        self.calls = 0
         self.ones = torch.ones(E, dtype=torch.bool, device=dev)
         self.zeros = torch.zeros(E, dtype=torch.bool, device=dev)
         self.load_state()
 
-    def load_state(self):
-        t, d = self.task, self.d
+    def load_state(self, k=0):
+        t, d = self.task, self.sets_d[k % len(self.sets_d)]
         t.left_finger_pos, t.right_finger_pos, t.middle_finger_pos = d["fpos"][:, 0], d["fpos"][:, 1], d["fpos"][:, 2]
         t.left_finger_quat, t.right_finger_quat, t.middle_finger_quat = d["fquat"][:, 0], d["fquat"][:, 1], d["fquat"][:, 2]
         t.plug_pos, t.plug_quat = d["ppos"], d["pquat"]
@@ -298,6 +312,9 @@ class Workload:
 
     def step(self):
         t = self.task
+        if len(self.sets_d) > 1:
+            self.load_state(self.calls)      # attribute swaps only: no copy, no launch
+        self.calls += 1
         if t.pcl_cam:
             t.invalidate_socket_cache()   # worst case: every env restarted -> socket cloud recomputed each step
         # update_tactile + update_external_cam with the reference's mask arguments (task :862-887)
@@ -409,7 +426,7 @@ def main():
         return
 
     # ---- one size: the headline (obs4096) or a single-path config ----------------------------------------------
-    wl = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=args.falloff)
+    wl = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=args.falloff, two_sets=not args.one_input_set)
     task = wl.task
     gather, gather_note = None, None
     if world > 1:
@@ -466,7 +483,8 @@ def main():
     extra = {}
     if tactile and world == 1 and not args.no_alt_falloff:
         other = "none" if (args.falloff or "inverse_square") == "inverse_square" else "inverse_square"
-        wl2 = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=other, pin=False)
+        wl2 = Workload(E, offset, total, dev, args, tactile=tactile, pcl=pcl, falloff=other, pin=False,
+                       two_sets=not args.one_input_set)
         ms2 = timed(lambda i: wl2.step(), args.steps, W) / args.steps
         t2 = timed(lambda i: wl2.task.update_tactile(wl2.ones, wl2.ones), max(args.steps // 2, 5), 3) / max(args.steps // 2, 5)
         extra["alt_falloff"] = {"falloff": other, "ms_per_step": ms2, "value": total / (ms2 * 1e-3), "unit": UNIT,
@@ -578,9 +596,9 @@ def main():
         E2E_DEPTH = _pl.SLOTS - 1
         pipe = HostObsPipeline(task, sampler_socket_every_step=True)
         handles = []
-        h = wl.h
 
         def e2e_step(i):
+            h = wl.sets_h[i % len(wl.sets_h)]
             # host buffers in, host result out, every step: upload / kernels / download of
             # neighbouring steps overlap on three streams (isaacgyminsertion_b200.pipeline)
             if gather is not None:
@@ -600,7 +618,7 @@ def main():
             finish()
         ms_e2e = timed(e2e_step, K, 3, after=e2e_finish)
         e2e = {"value": total * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.last_h2d_bytes,
-               "seg_host_dtype": str(h["seg"].dtype).replace("torch.", ""),
+               "seg_host_dtype": str(wl.sets_h[0]["seg"].dtype).replace("torch.", ""),
                "d2h_bytes_per_step": pipe.d2h_bytes, "ms_per_step": ms_e2e / K, "steps": K,
                "overlap": "upload / kernels / download of neighbouring steps on 3 streams, 3-slot ring",
                "numa": numa}
@@ -623,6 +641,8 @@ def main():
                                    f"sampler={args.sampler}, socket cloud recomputed every step",
                        "config": cfg, "envs_per_gpu": E, "total_envs": total, "sensors_per_env": 3, "sampler": args.sampler,
                        "falloff": args.falloff or "inverse_square (shipped yaml)",
+                       "inputs": ("one seeded set of poses / camera frames" if args.one_input_set else
+                                  "two seeded sets of poses / camera frames, alternating every step"),
                        "l2": "per-step outputs (4.4 GB at 4096 envs) and depth/seg inputs (170 MB) exceed the 126 MB L2",
                        "gather": ("none" if world == 1 else f"{args.gather}, " + ("sync" if args.sync_gather else "overlapped"))},
             "clocks": sampler.summary(),
