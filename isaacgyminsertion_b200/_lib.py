@@ -54,6 +54,29 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
+class on_device:
+    """`with on_device(dev):` makes `dev` the current CUDA device for the launches inside when it is not already
+    (an engine may live on a device other than the caller's current one); a no-op otherwise."""
+
+    def __init__(self, device):
+        d = torch.device(device) if not isinstance(device, torch.device) else device
+        self.idx = d.index
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def stream_ptr(device=None):
     return _P(torch.cuda.current_stream(device).cuda_stream)
 

@@ -302,7 +302,7 @@ class BatchedAllSight:
         self._hiz_layout = ([0], [1])
         self._sensor = self._sensor_params(np.zeros(3, np.float32), 1.0, 1.0, (1, 1, 1), 1.0)
         zbuf = torch.empty((H * W,), dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = self.lib.igi_tactile_gel_precompute(_c.byref(self._sensor), _lib.dptr(self._dxp), _lib.dptr(self._dyp),
                                                      _lib.dptr(self._gel), _c.c_int(self._gel.shape[0]), _lib.dptr(zbuf),
                                                      _lib.dptr(self.depth0), _lib.dptr(self.bg_sim),
@@ -336,8 +336,9 @@ class BatchedAllSight:
         # obs of a frame without contact (color == bg_real): exact for every background id
         self.obs_empty = torch.empty((OBS_LEN,), dtype=torch.float32, device=dev)
         zero_id = torch.zeros((1,), dtype=torch.int32, device=dev)
-        rc = self.lib.igi_tactile_obs(_lib.dptr(self.bg_real), _lib.dptr(self.bg_real), _lib.dptr(zero_id), _c.c_int(1),
-                                      _lib.dptr(self.obs_empty), _c.c_int64(OBS_LEN), _lib.stream_ptr(dev))
+        with _lib.on_device(dev):
+            rc = self.lib.igi_tactile_obs(_lib.dptr(self.bg_real), _lib.dptr(self.bg_real), _lib.dptr(zero_id), _c.c_int(1),
+                                          _lib.dptr(self.obs_empty), _c.c_int64(OBS_LEN), _lib.stream_ptr(dev))
         _lib.check(rc, "igi_tactile_obs")
         self._structs()
         self._handles = None
@@ -465,7 +466,7 @@ class BatchedAllSight:
         out = IgiTactileOut()
         out.color, out.gel_depth, out.obs = self.color.data_ptr(), self.gel_depth.data_ptr(), obs.data_ptr()
         out.obs_env_stride, out.obs_sensor_stride = obs.stride(0), obs.stride(1)
-        with torch.cuda.device(self.device):
+        with _lib.on_device(self.device):
             rc = self.lib.igi_tactile_render(_c.byref(self._sensor), _c.byref(self._m), _c.byref(self._st), _c.byref(fr),
                                              _c.byref(self._sc), _c.byref(out), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_tactile_render")

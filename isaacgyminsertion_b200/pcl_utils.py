@@ -194,13 +194,14 @@ class BatchedPointCloud:
         cnt = self._buf(tag + "_cnt", (n, C), torch.int32)
         any_ = self._buf(tag + "_any", (n, C), torch.int32)
         box_arr = _lib.carr(_c.c_float, box) if box is not None else None
-        rc = self.lib.igi_pcl_compact(
-            _lib.dptr(depth, torch.float32, "depth"), _lib.dptr(seg, torch.int32, "seg"),
-            _lib.carr(_c.c_int32, [int(s) for s in seg_ids]), _c.c_int(C),
-            _lib.dptr(uvx), _lib.dptr(uvy), _lib.dptr(uvz), _lib.dptr(ext), _lib.dptr(e2g),
-            _c.c_int(n), _c.c_int(self.H), _c.c_int(self.W),
-            _c.c_float(-1.0 if self.depth_max is None else float(self.depth_max)),
-            box_arr, _lib.dptr(pts), _lib.dptr(cnt), _lib.dptr(any_), _lib.stream_ptr(self.device))
+        with _lib.on_device(self.device):
+            rc = self.lib.igi_pcl_compact(
+                _lib.dptr(depth, torch.float32, "depth"), _lib.dptr(seg, torch.int32, "seg"),
+                _lib.carr(_c.c_int32, [int(s) for s in seg_ids]), _c.c_int(C),
+                _lib.dptr(uvx), _lib.dptr(uvy), _lib.dptr(uvz), _lib.dptr(ext), _lib.dptr(e2g),
+                _c.c_int(n), _c.c_int(self.H), _c.c_int(self.W),
+                _c.c_float(-1.0 if self.depth_max is None else float(self.depth_max)),
+                box_arr, _lib.dptr(pts), _lib.dptr(cnt), _lib.dptr(any_), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_pcl_compact")
         return pts, cnt, any_
 
@@ -231,11 +232,12 @@ class BatchedPointCloud:
         idx = torch.empty((n, m), dtype=torch.int32, device=self.device) if return_idx else None
         consumed = self._buf("consumed", (1,), torch.int32)
         offs = self._buf("offs", (n,), torch.int32)
-        rc = self.lib.igi_pcl_sample_gather(
-            _lib.dptr(pts, torch.float32), _lib.dptr(cnt, torch.int32), _lib.dptr(any_, torch.int32),
-            _c.c_int(C), _c.c_int(cls), _c.c_int(cap), _lib.dptr(raw), _c.c_int(n), _c.c_int(m),
-            _c.c_void_p(out.data_ptr()), _c.c_int64(out.stride(0)), _lib.dptr(idx), _lib.dptr(consumed),
-            _lib.dptr(offs), _lib.stream_ptr(self.device))
+        with _lib.on_device(self.device):
+            rc = self.lib.igi_pcl_sample_gather(
+                _lib.dptr(pts, torch.float32), _lib.dptr(cnt, torch.int32), _lib.dptr(any_, torch.int32),
+                _c.c_int(C), _c.c_int(cls), _c.c_int(cap), _lib.dptr(raw), _c.c_int(n), _c.c_int(m),
+                _c.c_void_p(out.data_ptr()), _c.c_int64(out.stride(0)), _lib.dptr(idx), _lib.dptr(consumed),
+                _lib.dptr(offs), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_pcl_sample_gather")
         if strict_rng:
             self.rng_stream.commit(total_words if self.sharded else int(consumed.item()))
@@ -263,11 +265,12 @@ class BatchedPointCloud:
             assert out.stride(0) == C * out_stride, "all-class output must be dense over (env, class)"
         idx = torch.empty(shape[:-1], dtype=torch.int32, device=self.device) if return_idx else None
         scratch = self._buf("fps_sched", (n_tasks + 8,), torch.int32)
-        rc = self.lib.igi_fps_balanced(
-            _c.c_void_p(p0.data_ptr()), _c.c_int64(task_stride),
-            _c.c_void_p(c0.data_ptr()), _c.c_void_p(a0.data_ptr()), _c.c_int64(count_stride),
-            _c.c_int(n_tasks), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out_stride),
-            _lib.dptr(idx), _lib.dptr(scratch), _c.c_int(flags), _lib.stream_ptr(self.device))
+        with _lib.on_device(self.device):
+            rc = self.lib.igi_fps_balanced(
+                _c.c_void_p(p0.data_ptr()), _c.c_int64(task_stride),
+                _c.c_void_p(c0.data_ptr()), _c.c_void_p(a0.data_ptr()), _c.c_int64(count_stride),
+                _c.c_int(n_tasks), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out_stride),
+                _lib.dptr(idx), _lib.dptr(scratch), _c.c_int(flags), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_fps_balanced")
         return (out, idx) if return_idx else out
 
@@ -280,11 +283,12 @@ class BatchedPointCloud:
         assert out.stride(-1) == 1 and out.stride(-2) == 3
         idx = torch.empty((n, m), dtype=torch.int32, device=self.device) if return_idx else None
         p0 = pts[:, cls]
-        rc = self.lib.igi_fps(
-            _c.c_void_p(p0.data_ptr()), _c.c_int64(pts.stride(0)),
-            _c.c_void_p(cnt[:, cls].data_ptr()), _c.c_void_p(any_[:, cls].data_ptr()), _c.c_int64(C),
-            _c.c_int(0), _c.c_int(n), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out.stride(0)),
-            _lib.dptr(idx), _c.c_int(0), _lib.stream_ptr(self.device))
+        with _lib.on_device(self.device):
+            rc = self.lib.igi_fps(
+                _c.c_void_p(p0.data_ptr()), _c.c_int64(pts.stride(0)),
+                _c.c_void_p(cnt[:, cls].data_ptr()), _c.c_void_p(any_[:, cls].data_ptr()), _c.c_int64(C),
+                _c.c_int(0), _c.c_int(n), _c.c_int(m), _c.c_void_p(out.data_ptr()), _c.c_int64(out.stride(0)),
+                _lib.dptr(idx), _c.c_int(0), _lib.stream_ptr(self.device))
         _lib.check(rc, "igi_fps")
         return (out, idx) if return_idx else out
 
@@ -297,9 +301,10 @@ def furthest_point_sample(xyz, npoint, flags=0):
     B, N, _ = xyz.shape
     xyz = xyz.contiguous()
     idx = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
-    rc = lib.igi_fps(_lib.dptr(xyz, torch.float32, "xyz"), _c.c_int64(N * 3), None, None, _c.c_int64(1),
-                     _c.c_int(N), _c.c_int(B), _c.c_int(npoint), None, _c.c_int64(npoint * 3),
-                     _lib.dptr(idx), _c.c_int(flags), _lib.stream_ptr(xyz.device))
+    with _lib.on_device(xyz.device):
+        rc = lib.igi_fps(_lib.dptr(xyz, torch.float32, "xyz"), _c.c_int64(N * 3), None, None, _c.c_int64(1),
+                         _c.c_int(N), _c.c_int(B), _c.c_int(npoint), None, _c.c_int64(npoint * 3),
+                         _lib.dptr(idx), _c.c_int(flags), _lib.stream_ptr(xyz.device))
     _lib.check(rc, "igi_fps")
     return idx
 

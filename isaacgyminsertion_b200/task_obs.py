@@ -144,10 +144,11 @@ class FactoryTaskInsertionTactileObs:
         self.tactile_engine.render(fpos, fquat, self._dense(self.plug_pos), self._dense(self.plug_quat),
                                    force=force, update=update_freq, update2=update_delay, obs_out=self.tactile_imgs)
         # tactile_queue[:, 1:] = tactile_queue[:, :-1]; tactile_queue[:, 0] = tactile_imgs   (:512-513)
-        _lib.check(self._lib.igi_queue_push(
-            _c.c_void_p(self.tactile_queue.data_ptr()), _c.c_void_p(self.tactile_imgs.data_ptr()), _c.c_int(0),
-            _c.c_int64(self.obs_packed.stride(0)), _c.c_int(self.num_envs), _c.c_int(self.tactile_queue.shape[1]),
-            _c.c_longlong(TACTILE_FLOATS), _lib.stream_ptr(self.device)), "igi_queue_push")
+        with _lib.on_device(self.device):
+            _lib.check(self._lib.igi_queue_push(
+                _c.c_void_p(self.tactile_queue.data_ptr()), _c.c_void_p(self.tactile_imgs.data_ptr()), _c.c_int(0),
+                _c.c_int64(self.obs_packed.stride(0)), _c.c_int(self.num_envs), _c.c_int(self.tactile_queue.shape[1]),
+                _c.c_longlong(TACTILE_FLOATS), _lib.stream_ptr(self.device)), "igi_queue_push")
 
     @staticmethod
     def _dense(t):
@@ -188,19 +189,21 @@ class FactoryTaskInsertionTactileObs:
         compute_socket = bool(self._socket_pending)
         f, d, sd = self._u8(update_freq), self._u8(update_delay), self._u8(seg_update_delay)
         # upd_seg = freq & seg_delay; restarted = socket pending & got_socket == 0 (-> 1); upd_pcl = freq & delay | restarted
-        _lib.check(lib.igi_cam_masks(
-            _c.c_void_p(f.data_ptr()), _c.c_void_p(d.data_ptr()), _c.c_void_p(sd.data_ptr()),
-            _c.c_void_p(self.got_socket.data_ptr()), _c.c_int((2 if self._socket_force else 1) if compute_socket else 0),
-            _c.c_void_p(self._upd_seg.data_ptr()), _c.c_void_p(self._upd_pcl.data_ptr()),
-            _c.c_void_p(self._restarted.data_ptr()), _c.c_int(N), st), "igi_cam_masks")
+        with _lib.on_device(dev):
+            _lib.check(lib.igi_cam_masks(
+                _c.c_void_p(f.data_ptr()), _c.c_void_p(d.data_ptr()), _c.c_void_p(sd.data_ptr()),
+                _c.c_void_p(self.got_socket.data_ptr()), _c.c_int((2 if self._socket_force else 1) if compute_socket else 0),
+                _c.c_void_p(self._upd_seg.data_ptr()), _c.c_void_p(self._upd_pcl.data_ptr()),
+                _c.c_void_p(self._restarted.data_ptr()), _c.c_int(N), st), "igi_cam_masks")
         segf = seg.reshape(N, -1)
         if segf.dtype != torch.int32 or not segf.is_contiguous():
             segf = segf.to(torch.int32).contiguous()
         row = self.seg_buf.shape[1] * 4
-        _lib.check(lib.igi_copy_rows_where(                                                        # :934-940
-            _c.c_void_p(self.seg_buf.data_ptr()), _c.c_longlong(row), _c.c_void_p(segf.data_ptr()), _c.c_longlong(row),
-            _c.c_void_p(self._upd_seg.data_ptr()), _c.c_int(1), _c.c_longlong(N), _c.c_longlong(row), st),
-            "igi_copy_rows_where")
+        with _lib.on_device(dev):
+            _lib.check(lib.igi_copy_rows_where(                                                        # :934-940
+                _c.c_void_p(self.seg_buf.data_ptr()), _c.c_longlong(row), _c.c_void_p(segf.data_ptr()), _c.c_longlong(row),
+                _c.c_void_p(self._upd_seg.data_ptr()), _c.c_int(1), _c.c_longlong(N), _c.c_longlong(row), st),
+                "igi_copy_rows_where")
         gen = self.pcl_generator
         box = filter_pts.box
         all_pts = None
@@ -239,10 +242,11 @@ class FactoryTaskInsertionTactileObs:
         else:
             merged = torch.cat([plug_pts, self.socket_pcl], dim=1).flatten(start_dim=1)
         # pcl[update] = merged[update] (:1027); pcl_queue[:, 1:] = pcl_queue[:, :-1]; pcl_queue[:, 0] = pcl (:1046-1048)
-        _lib.check(lib.igi_pcl_assemble(
-            _c.c_void_p(merged.data_ptr()), _c.c_int64(merged.stride(0)), _c.c_void_p(self.pcl.data_ptr()),
-            _c.c_int64(self.pcl.stride(0)), _c.c_void_p(self._upd_pcl.data_ptr()), _c.c_void_p(self.pcl_queue.data_ptr()),
-            _c.c_int(N), _c.c_int(self.pcl_queue.shape[1]), _c.c_longlong(self.pcl_floats), st), "igi_pcl_assemble")
+        with _lib.on_device(dev):
+            _lib.check(lib.igi_pcl_assemble(
+                _c.c_void_p(merged.data_ptr()), _c.c_int64(merged.stride(0)), _c.c_void_p(self.pcl.data_ptr()),
+                _c.c_int64(self.pcl.stride(0)), _c.c_void_p(self._upd_pcl.data_ptr()), _c.c_void_p(self.pcl_queue.data_ptr()),
+                _c.c_int(N), _c.c_int(self.pcl_queue.shape[1]), _c.c_longlong(self.pcl_floats), st), "igi_pcl_assemble")
 
     def invalidate_socket_cache(self):
         """Every env recomputes its socket cloud on the next step (what a reset of all envs does to got_socket),

@@ -99,3 +99,32 @@ def test_gathered_rows_equal_single_gpu_rows(built_lib, world):
         assert same, f"{key}: gathered rows differ from the single-GPU rows at world={world}"
         assert nonzero == total, f"{key}: {nonzero} of {total} rows populated"
     assert set(res) == {(s, t) for s in ("fps", "reference") for t in ("nccl", "p2p")}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus N)")
+def test_engines_on_two_devices_in_one_process(built_lib):
+    """One process, current device cuda:0, task objects on cuda:0 and cuda:1: same rows on both (function attributes
+    are set per device, launches run under a device guard, no library state is shared)."""
+    import numpy as np
+    import bench
+    from isaacgyminsertion_b200.task_obs import FactoryTaskInsertionTactileObs
+    n = 12
+    gym, P, depth, seg = bench.make_inputs(n, 0, n)
+    torch.cuda.set_device(0)
+    rows = []
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):
+        task = FactoryTaskInsertionTactileObs(n, gym, P["mesh_id"], P["bg_id"], device=dev, sampler="fps", falloff="none")
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        fp, fq = t(P["finger_pos"]), t(P["finger_quat"])
+        task.left_finger_pos, task.right_finger_pos, task.middle_finger_pos = fp[:, 0], fp[:, 1], fp[:, 2]
+        task.left_finger_quat, task.right_finger_quat, task.middle_finger_quat = fq[:, 0], fq[:, 1], fq[:, 2]
+        task.plug_pos, task.plug_quat = t(P["plug_pos"]), t(P["plug_quat"])
+        task.cam_renders, task.seg_renders = t(depth), t(seg)
+        ones = torch.ones(n, dtype=torch.bool, device=dev)
+        zeros = torch.zeros(n, dtype=torch.bool, device=dev)
+        task.compute_observations(ones, ones, ones, ones, ones, zeros, zeros)
+        task.tactile_engine.check_overflow()
+        rows.append(task.obs_packed.cpu())
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(rows[0], rows[1]) and torch.equal(rows[0], rows[2])
+    assert float(rows[0].abs().sum(1).min()) > 0
