@@ -35,14 +35,11 @@ struct CompactParams {
 // for 54x96) are staged into shared memory with two 1-D bulk async copies (TMA
 // engine) that complete on an mbarrier; every class (plug, socket) is then
 // produced from the staged tile, so HBM sees each input byte once.
-// Compaction keeps row-major pixel order (pcl_utils.py:71-72 boolean indexing).  A lane owns 4
-// consecutive pixels (one 128-bit shared load of depth, one of seg), a warp 128:
-//   phase A  lanes unproject / transform / box-test only their pixels of a wanted class (most of the
-//            image is background: two compares per pixel) and leave a 4-bit keep mask per class
-//   scan     ONE block-wide exclusive scan per class pair: a thread owns consecutive entries and the two
-//            classes' kept counts travel packed in one 32-bit word (two barriers per pair)
-//   phase B  threads recompute their kept points (same instruction sequence, same bits) and store them
-//            at their offsets
+// Compaction keeps row-major pixel order (pcl_utils.py:71-72 boolean indexing); a thread owns a run of
+// consecutive pixels, so thread order = pixel order:
+//   pass 1   an ordered list of the pixels of the wanted class (two compares per image pixel, one block scan)
+//   pass 2   the listed pixels are unprojected / transformed / box-tested on dense lanes and the kept points
+//            stored at their ordered offsets (one block scan per chunk of 512 list entries)
 struct CompactEval {
   const float* A;   // ext, row-vector: w = [px,py,pz,1] @ A
   const float* B;   // inverse(env_to_global): o = w @ B^T
@@ -74,24 +71,44 @@ struct CompactEval {
   }
 };
 
+// Block-wide exclusive scan of one int per thread (kCompactBlock threads, thread order); `total` = the sum.
+__device__ __forceinline__ int compact_block_scan(int v, int* s_wsum, int& total) {
+  constexpr int NW = kCompactBlock / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, sft);
+    if (lane >= sft) incl += t;
+  }
+  __syncthreads();   // the previous scan's readers of s_wsum are done
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  total = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const int t = s_wsum[w];
+    if (w < warp) woff += t;
+    total += t;
+  }
+  return woff + incl - v;
+}
+
 __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NW = kCompactBlock / 32;
   const int npix = p.H * p.W;
-  const int nq = (npix + 3) >> 2;                       // 4-pixel entries
   const int seg_off = (npix * 4 + 15) & ~15;
   float* s_depth = reinterpret_cast<float*>(smem_raw);
   int32_t* s_seg = reinterpret_cast<int32_t*>(smem_raw + seg_off);
-  // per entry: keep masks (4 bits per class), then per class its exclusive output offset
-  uint16_t* s_keep = reinterpret_cast<uint16_t*>(smem_raw + 2 * (size_t)seg_off);
+  uint16_t* s_idx = reinterpret_cast<uint16_t*>(smem_raw + 2 * (size_t)seg_off);   // ordered list of the pixels to evaluate
   __shared__ uint64_t s_bar;
   __shared__ int s_wsum[NW];
-  __shared__ int s_warp_any[NW];
   __shared__ float s_m[32];  // ext (16) + e2g_inv (16)
 
   const int env = blockIdx.x;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
   const float* g_depth = p.depth + (size_t)env * npix;
   const int32_t* g_seg = p.seg ? p.seg + (size_t)env * npix : nullptr;
 
@@ -128,9 +145,6 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
   ev.inv_w = 0xffffffffu / (uint32_t)p.W + 1u;
 #pragma unroll
   for (int k = 0; k < 6; ++k) ev.box[k] = p.box[k];
-  int sid[kMaxClasses];
-#pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c) sid[c] = p.seg_ids[c];
   const int NC = p.n_classes;
 
   // A masked-out pixel with finite depth becomes d = +-0 (pcl_utils.py / task :956-959) and maps to the
@@ -149,106 +163,64 @@ __global__ void __launch_bounds__(kCompactBlock) pcl_compact_kernel(CompactParam
     zero_kept = (o[0] >= p.box[0]) && (o[0] <= p.box[1]) && (o[1] >= p.box[2]) && (o[1] <= p.box[3]) &&
                 (o[2] >= p.box[4]) && (o[2] <= p.box[5]);
   }
+  const bool every_pixel = !g_seg || zero_kept;
 
-  // ---- phase A: keep masks.  Entry q = pixels 4q .. 4q+3; thread tid owns entries tid, tid + 256, ...
-  uint32_t anybits = 0;  // bit c: this thread kept a point of class c with a non-zero coordinate
-  for (int q = tid; q < nq; q += kCompactBlock) {
-    const float4 d4 = reinterpret_cast<const float4*>(s_depth)[q];
-    int4 s4 = make_int4(0, 0, 0, 0);
-    if (g_seg) s4 = reinterpret_cast<const int4*>(s_seg)[q];
-    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-    const int sg[4] = {s4.x, s4.y, s4.z, s4.w};
-    uint32_t keep = 0;
+  // Thread t owns the consecutive pixels [t*ppt, (t+1)*ppt): thread order = row-major pixel order, which both
+  // ordered compactions below keep (pcl_utils.py:71-72 boolean indexing).
+  const int ppt = (npix + kCompactBlock - 1) / kCompactBlock;
+  const int i_lo = min(tid * ppt, npix), i_hi = min(i_lo + ppt, npix);
+  constexpr int R = 2;   // list entries per thread and pass-2 chunk
+  for (int c = 0; c < NC; ++c) {
+    const int sid_c = p.seg_ids[c];
+    // ---- pass 1: the ordered list of the pixels of this class (two compares per image pixel; the plug / socket
+    // blobs are ~7 % of the image, so everything after this pass runs on dense lanes)
+    int cnt = 0;
+    if (every_pixel) cnt = i_hi - i_lo;
+    else for (int i = i_lo; i < i_hi; ++i) cnt += (s_seg[i] == sid_c) ? 1 : 0;
+    int n_list;
+    int off = compact_block_scan(cnt, s_wsum, n_list);
+    if (every_pixel) { for (int i = i_lo; i < i_hi; ++i) s_idx[off++] = (uint16_t)i; }
+    else { for (int i = i_lo; i < i_hi; ++i) if (s_seg[i] == sid_c) s_idx[off++] = (uint16_t)i; }
+    __syncthreads();
+    // ---- pass 2: unproject / transform / box-test the listed pixels, R consecutive entries per thread and chunk,
+    // and store the kept points at their ordered offsets (one block scan per chunk; plug and socket need one chunk)
+    float* out = p.out_pts + ((size_t)env * NC + c) * (size_t)npix * 3;
+    int base = 0;
+    bool nz = false;   // this thread kept a point with a non-zero coordinate (pcl_utils.py:179 `pts.any()`)
+    for (int j0 = 0; j0 < n_list; j0 += kCompactBlock * R) {
+      float o[R][3];
+      int keep = 0;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) {
-      if (c >= NC) break;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = 4 * q + k;
-        const bool mine = g_seg ? sg[k] == sid[c] : true;
-        if (i < npix && (mine || zero_kept)) {
-          const float dd = g_seg ? __fmul_rn(d[k], mine ? 1.0f : 0.0f) : d[k];  // -inf*0 = NaN, finite*0 = -0
-          float o[3];
-          if (ev(i, dd, o)) {
-            keep |= 1u << (4 * c + k);
-            if ((o[0] != 0.0f) | (o[1] != 0.0f) | (o[2] != 0.0f)) anybits |= 1u << c;
+      for (int r = 0; r < R; ++r) {
+        const int j = j0 + tid * R + r;
+        if (j < n_list) {
+          const int i = s_idx[j];
+          float dd = s_depth[i];
+          if (g_seg) dd = __fmul_rn(dd, s_seg[i] == sid_c ? 1.0f : 0.0f);   // -inf*0 = NaN, finite*0 = -0
+          if (ev(i, dd, o[r])) {
+            keep |= 1 << r;
+            nz = nz || (o[r][0] != 0.0f) || (o[r][1] != 0.0f) || (o[r][2] != 0.0f);
           }
         }
       }
-    }
-    s_keep[q] = (uint16_t)keep;
-  }
-  {
-    uint32_t wany = 0;
-    for (int c = 0; c < NC; ++c)
-      if (__any_sync(0xffffffffu, (anybits >> c) & 1u)) wany |= 1u << c;
-    if (lane == 0) s_warp_any[warp] = (int)wany;
-  }
-  __syncthreads();
-
-  // ---- ONE block scan for up to two classes at a time: thread t owns the consecutive entries
-  // [t*ept, (t+1)*ept) - pixel order = thread order - and the kept counts of a class pair travel packed in one
-  // 32-bit word (16 bits each: a class keeps fewer than 65536 points), so the whole compaction costs two
-  // barriers per class pair instead of three per 256 entries per class.  Phase B then walks the thread's
-  // entries in order and stores the kept points at the thread's offsets.
-  const int ept = (nq + kCompactBlock - 1) / kCompactBlock;
-  const int q_lo = min(tid * ept, nq), q_hi = min(q_lo + ept, nq);
-  for (int c0 = 0; c0 < NC; c0 += 2) {
-    uint32_t packed = 0;
-    for (int q = q_lo; q < q_hi; ++q) {
-      const uint32_t k = s_keep[q];
-      packed += (uint32_t)__popc((k >> (4 * c0)) & 15u);
-      if (c0 + 1 < NC) packed += (uint32_t)__popc((k >> (4 * c0 + 4)) & 15u) << 16;
-    }
-    uint32_t incl = packed;
+      int kept;
+      int slot = base + compact_block_scan(__popc(keep), s_wsum, kept);
 #pragma unroll
-    for (int sft = 1; sft < 32; sft <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, sft);
-      if (lane >= sft) incl += t;
-    }
-    __syncthreads();   // the previous pair's readers of s_wsum are done
-    if (lane == 31) s_wsum[warp] = (int)incl;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const uint32_t t = (uint32_t)s_wsum[w];
-      if (w < warp) woff += t;
-      total += t;
-    }
-    const uint32_t excl = woff + incl - packed;
-    for (int cc = 0; cc < 2 && c0 + cc < NC; ++cc) {
-      const int c = c0 + cc;
-      float* out = p.out_pts + ((size_t)env * NC + c) * (size_t)npix * 3;
-      const int sid_c = p.seg_ids[c];
-      int slot = (int)((excl >> (16 * cc)) & 0xffffu);
-      for (int q = q_lo; q < q_hi; ++q) {
-        const uint32_t m = (s_keep[q] >> (4 * c)) & 15u;
-        if (!m) continue;
-        const float4 d4 = reinterpret_cast<const float4*>(s_depth)[q];
-        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!((m >> k) & 1u)) continue;
-          const int i = 4 * q + k;
-          float dd = d[k];
-          if (g_seg) dd = __fmul_rn(dd, s_seg[i] == sid_c ? 1.0f : 0.0f);
-          float o[3];
-          ev(i, dd, o);
+      for (int r = 0; r < R; ++r) {
+        if ((keep >> r) & 1) {
           float* dst = out + (size_t)slot * 3;
-          dst[0] = o[0];
-          dst[1] = o[1];
-          dst[2] = o[2];
+          dst[0] = o[r][0];
+          dst[1] = o[r][1];
+          dst[2] = o[r][2];
           ++slot;
         }
       }
-      if (tid == 0) {
-        int bany = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) bany |= (s_warp_any[w] >> c) & 1;
-        p.out_count[(size_t)env * NC + c] = (int)((total >> (16 * cc)) & 0xffffu);
-        p.out_any[(size_t)env * NC + c] = bany;
-      }
+      base += kept;
+    }
+    const int bany = __syncthreads_or(nz ? 1 : 0);   // also: every reader of s_idx is done before the next class rewrites it
+    if (tid == 0) {
+      p.out_count[(size_t)env * NC + c] = base;
+      p.out_any[(size_t)env * NC + c] = bany ? 1 : 0;
     }
   }
 }
@@ -938,7 +910,7 @@ extern "C" int igi_pcl_compact(const float* depth, const int32_t* seg, const int
   p.has_box = box != nullptr;
   if (box) for (int i = 0; i < 6; ++i) p.box[i] = box[i];
   const size_t npix = (size_t)H * W;
-  const size_t smem = 2 * ((npix * 4 + 15) & ~(size_t)15) + ((npix + 3) / 4) * 2 + 16;
+  const size_t smem = 2 * ((npix * 4 + 15) & ~(size_t)15) + npix * 2 + 16;   // depth, seg, u16 pixel list
   IGI_REQUIRE(smem <= 200 * 1024 && npix < 65536, "igi_pcl_compact: image too large for one CTA (%d x %d)", H, W);
   p.use_bulk = ((npix * 4) % 16 == 0) && ((uintptr_t)depth % 16 == 0) && (!seg || (uintptr_t)seg % 16 == 0);
   {   // the opt-in shared-memory size is a per-DEVICE function attribute
