@@ -13,9 +13,9 @@ for cfg in tactile1024 pcl1024 sweep small; do
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/f_${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-alt-falloff > gpurun_out/f_${tag}_ncu_bench.log 2>&1
 python tools/launches.py gpurun_out/f_${tag}_launches.csv 12
-for k in tac_contact tac_geom; do
+for k in tac_contact tac_geom pcl_compact_kernel fps_sorted_kernel; do
   ncu --set full --clock-control none --import-source on --kernel-name regex:$k --launch-skip 2 --launch-count 1 \
       -f -o gpurun_out/f_${tag}_ncu_$k python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-components --no-alt-falloff > gpurun_out/f_${tag}_ncu_$k.log 2>&1
 done
-python tools/ncu_summary.py gpurun_out/f_${tag}_ncu_tac_contact.ncu-rep gpurun_out/f_${tag}_ncu_tac_geom.ncu-rep > gpurun_out/f_${tag}_ncu_full.txt 2>&1
+python tools/ncu_summary.py gpurun_out/f_${tag}_ncu_tac_contact.ncu-rep gpurun_out/f_${tag}_ncu_tac_geom.ncu-rep gpurun_out/f_${tag}_ncu_pcl_compact_kernel.ncu-rep gpurun_out/f_${tag}_ncu_fps_sorted_kernel.ncu-rep > gpurun_out/f_${tag}_ncu_full.txt 2>&1
 grep -E "dram__bytes|gpu__time_duration|smsp__inst_executed.sum|issue_active" gpurun_out/f_${tag}_ncu_full.txt
