@@ -292,6 +292,11 @@ __global__ void __launch_bounds__(128) pcl_gather_kernel(const float* pts, const
 constexpr int kFpsBlock = 128;
 
 __device__ __forceinline__ uint32_t bitrev_n(uint32_t v, int bits) { return __brev(v) >> (32 - bits); }
+// a*a + b*b + c*c in the form nvcc's default -fmad=true gives the published kernel's source expression
+// (mul(b,b), fma(a,a,.), fma(c,c,.) — oracle/fps.c header); oracle/fps.c evaluates the same three operations.
+__device__ __forceinline__ float fps_sumsq(float a, float b, float c) {
+  return __fmaf_rn(c, c, __fmaf_rn(a, a, __fmul_rn(b, b)));
+}
 
 // Candidate ordering: larger distance wins; among equal distances the upstream
 // block reduction keeps the candidate of the thread whose id has the smaller
@@ -361,10 +366,10 @@ __global__ void __launch_bounds__(kFpsBlock) fps_kernel(const float* pts, int64_
       uint32_t bhi = 0, blo = 0;
       for (int k = tid; k < n; k += kFpsBlock) {
         const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
-        const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+        const float mag = fps_sumsq(x2, y2, z2);
         if (mag <= 1e-3f) continue;
         const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float d = fps_sumsq(dx, dy, dz);
         const float d2 = fminf(d, st[k]);
         st[k] = d2;
         const uint32_t hi = __float_as_uint(d2) + 1u;
@@ -434,7 +439,7 @@ __device__ __forceinline__ void fps_init_state(const float* sx, const float* sy,
     lokey[i] = 0u;
     if (k < n) {
       const float x2 = sx[k], y2 = sy[k], z2 = sz[k];
-      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+      const float mag = fps_sumsq(x2, y2, z2);
       if (mag > 1e-3f) {
         temp[i] = 1e10f;
         lokey[i] = fps_tie_key(k, lg, bmask);
@@ -453,8 +458,41 @@ __device__ __forceinline__ float fps_update(const float* sx, const float* sy, co
   for (int i = 0; i < PPL; ++i) {
     const int k = first + stride * i;   // planes are padded: reads beyond n are harmless (min with -1 stays -1)
     const float dx = __fsub_rn(sx[k], x1), dy = __fsub_rn(sy[k], y1), dz = __fsub_rn(sz[k], z1);
-    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const float d = fps_sumsq(dx, dy, dz);
     const float d2 = fminf(d, temp[i]);
+    temp[i] = d2;
+    best = fmaxf(best, d2);
+  }
+  return best;
+}
+
+// One pick's distance update for PPL register-resident points against (x1,y1,z1); returns the thread's best minimum.
+// FPS_F32X2: two points per instruction with Blackwell's packed f32x2 add / mul / fma (each half rounds to nearest
+// like the scalar operation: x - x1 == x + (-x1) exactly, so results do not change bit for bit).
+template <int PPL>
+__device__ __forceinline__ float fps_update_reg(const float* px, const float* py, const float* pz, float x1, float y1,
+                                                float z1, float* temp) {
+  float best = -1.0f;
+#ifdef FPS_F32X2
+  const float2 nx = make_float2(-x1, -x1), ny = make_float2(-y1, -y1), nz = make_float2(-z1, -z1);
+#pragma unroll
+  for (int i = 0; i + 1 < PPL; i += 2) {
+    const float2 dx = __fadd2_rn(make_float2(px[i], px[i + 1]), nx);
+    const float2 dy = __fadd2_rn(make_float2(py[i], py[i + 1]), ny);
+    const float2 dz = __fadd2_rn(make_float2(pz[i], pz[i + 1]), nz);
+    const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+    const float a = fminf(d.x, temp[i]), b = fminf(d.y, temp[i + 1]);
+    temp[i] = a; temp[i + 1] = b;
+    best = fmaxf(best, fmaxf(a, b));
+  }
+  constexpr int TAIL = PPL & ~1;
+#else
+  constexpr int TAIL = 0;
+#endif
+#pragma unroll
+  for (int i = TAIL; i < PPL; ++i) {
+    const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
+    const float d2 = fminf(fps_sumsq(dx, dy, dz), temp[i]);
     temp[i] = d2;
     best = fmaxf(best, d2);
   }
@@ -492,16 +530,7 @@ __device__ __forceinline__ void fps_warp_picks(const float* sx, const float* sy,
   for (; j < m; ++j) {
     float best;
     if (REG) {
-      const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-      best = -1.0f;
-#pragma unroll
-      for (int i = 0; i < PPL; ++i) {
-        const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
-        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const float d2 = fminf(d, temp[i]);
-        temp[i] = d2;
-        best = fmaxf(best, d2);
-      }
+      best = fps_update_reg<PPL>(px, py, pz, sx[old], sy[old], sz[old], temp);
     } else {
       best = fps_update<PPL>(sx, sy, sz, old, lane, 32, temp);
     }
@@ -552,16 +581,7 @@ __device__ __forceinline__ void fps_coop_picks(const FpsTaskArgs& a, int task, i
   }
   int j = 1;
   for (; j < m; ++j) {
-    const float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-    float best = -1.0f;
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) {
-      const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const float d2 = fminf(d, temp[i]);
-      temp[i] = d2;
-      best = fmaxf(best, d2);
-    }
+    const float best = fps_update_reg<PPL>(px, py, pz, sx[old], sy[old], sz[old], temp);
     const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));
     const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
     if (lane == 0) s_cand[j & 1][warp] = make_int2(wb, (int)wlo);
@@ -715,7 +735,7 @@ __device__ __forceinline__ void fps_cluster_picks(cg::cluster_group& cluster, co
     px[i] = 0.f; py[i] = 0.f; pz[i] = 0.f; temp[i] = -1.0f; lokey[i] = 0u;
     if (k < n) {
       px[i] = src[(size_t)k * 3 + 0]; py[i] = src[(size_t)k * 3 + 1]; pz[i] = src[(size_t)k * 3 + 2];
-      const float mag = __fadd_rn(__fadd_rn(__fmul_rn(px[i], px[i]), __fmul_rn(py[i], py[i])), __fmul_rn(pz[i], pz[i]));
+      const float mag = fps_sumsq(px[i], py[i], pz[i]);
       if (mag > 1e-3f) { temp[i] = 1e10f; lokey[i] = fps_tie_key(k, lg, bmask); }
     }
   }
@@ -728,15 +748,7 @@ __device__ __forceinline__ void fps_cluster_picks(cg::cluster_group& cluster, co
   }
   int j = 1;
   for (; j < m; ++j) {
-    float best = -1.0f;
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) {
-      const float dx = __fsub_rn(px[i], x1), dy = __fsub_rn(py[i], y1), dz = __fsub_rn(pz[i], z1);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const float d2 = fminf(d, temp[i]);
-      temp[i] = d2;
-      best = fmaxf(best, d2);
-    }
+    const float best = fps_update_reg<PPL>(px, py, pz, x1, y1, z1, temp);
     const int wb = __reduce_max_sync(0xffffffffu, __float_as_int(best));   // floats >= 0 order as ints; -1 < 0
     const uint32_t wlo = __reduce_max_sync(0xffffffffu, fps_tie<PPL>(temp, lokey, wb));
     // coordinates of the warp's candidate: the (unique) slot whose tie key is wlo

@@ -18,51 +18,46 @@ sampling_gpu.cu) from memory:
      candidates is therefore the one with the smallest bit-reversed (k mod B), then the
      smallest k.  No candidate at all -> index 0.
 
-Distances are f32 with every multiply/add rounded separately (no FMA contraction) — a
-decision of this repo, stated here and in DESIGN.md; the CUDA kernel uses the same
-non-contracted operations so indices can be compared bit-for-bit.
+Arithmetic: f32, in the form nvcc gives the published expressions under its default
+-fmad=true — `x*x + y*y + z*z` becomes mul(y,y), fma(x,x,.), fma(z,z,.) (checked here by
+compiling the two source lines with nvcc 12.9 and reading the PTX).  Python has no f32
+fma, so the loop lives in oracle/fps.c (explicit fmaf(), built with -ffp-contract=off by
+oracle/Makefile); this module is its loader plus the task-level emptiness rule.  The CUDA
+kernels use __fmul_rn/__fmaf_rn in the same order, so indices compare bit-for-bit.
+tests/test_oracle_pcl.py checks the C loop against a literal thread-by-thread emulation
+of the published kernel.
 """
+import ctypes
+import os
+import subprocess
+
 import numpy as np
 
+HERE = os.path.dirname(os.path.abspath(__file__))
+FPS_SO = os.path.join(HERE, "liboracle_fps.so")
+_lib = None
 
-def _bitrev(v, bits):
-    r = 0
-    for _ in range(bits):
-        r = (r << 1) | (v & 1)
-        v >>= 1
-    return r
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(FPS_SO):
+            subprocess.run(["make", "-C", HERE, "liboracle_fps.so"], check=True, stdout=subprocess.DEVNULL)
+        _lib = ctypes.CDLL(FPS_SO)
+        _lib.igi_oracle_fps.restype = ctypes.c_int
+        _lib.igi_oracle_fps.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    return _lib
 
 
 def furthest_point_sample(pts, m):
     """pts (n,3) f32 -> (m,) int32 indices."""
-    pts = np.ascontiguousarray(pts, dtype=np.float32)
-    n = pts.shape[0]
+    pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
     idx = np.zeros(m, dtype=np.int32)
-    if n == 0:
+    if pts.shape[0] == 0 or m == 0:
         return idx
-    lg = min(int(np.floor(np.log2(n))), 9)
-    B = 1 << lg
-    k = np.arange(n)
-    tiekey = np.array([(_bitrev(int(i) & (B - 1), lg) << 16) | int(i) for i in k], dtype=np.int64)
-    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
-    mag = (x * x + y * y) + z * z
-    cand = mag > np.float32(1e-3)
-    temp = np.full(n, np.float32(1e10), dtype=np.float32)
-    old = 0
-    for j in range(1, m):
-        dx = x - x[old]
-        dy = y - y[old]
-        dz = z - z[old]
-        d = (dx * dx + dy * dy) + dz * dz
-        d2 = np.minimum(d, temp)
-        temp = np.where(cand, d2, temp)
-        if not cand.any():
-            old = 0
-        else:
-            best = d2[cand].max()
-            tied = cand & (d2 == best)
-            old = int(k[tied][np.argmin(tiekey[tied])])
-        idx[j] = old
+    rc = _load().igi_oracle_fps(pts.ctypes.data, pts.shape[0], m, idx.ctypes.data)
+    if rc != 0:
+        raise MemoryError("igi_oracle_fps")
     return idx
 
 

@@ -130,10 +130,20 @@ def test_fps_oracle_degenerate():
     assert not out[0].any() and idx[1][1] == 3
 
 
+def _fmaf():
+    import ctypes, ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+    libm.fmaf.restype = ctypes.c_float
+    libm.fmaf.argtypes = [ctypes.c_float] * 3
+    return lambda a, b, c: np.float32(libm.fmaf(float(a), float(b), float(c)))
+
+
 def _fps_literal(pts, m):
     """Literal emulation of the published pointnet2_ops kernel (furthest_point_sampling_kernel): B threads stride over
     the points keeping the first maximum (strict >), then the shared-memory tree `__update(t, t + s)` for
-    s = B/2 .. 1, where a tie keeps the lower position.  Slow; small cases only."""
+    s = B/2 .. 1, where a tie keeps the lower position.  Sums of squares in nvcc's contraction of the source
+    expression (mul, fma, fma — oracle/fps.c header).  Slow; small cases only."""
+    fma = _fmaf()
     pts = np.ascontiguousarray(pts, dtype=np.float32)
     n = len(pts)
     B = 1 << min(int(np.floor(np.log2(n))), 9)
@@ -148,11 +158,11 @@ def _fps_literal(pts, m):
         for tid in range(B):
             for k in range(tid, n, B):
                 x2, y2, z2 = pts[k]
-                mag = f(f(x2 * x2) + f(y2 * y2)) + f(z2 * z2)
+                mag = fma(z2, z2, fma(x2, x2, f(y2 * y2)))
                 if mag <= f(1e-3):
                     continue
                 dx, dy, dz = f(x2 - x1), f(y2 - y1), f(z2 - z1)
-                d = f(f(f(dx * dx) + f(dy * dy)) + f(dz * dz))
+                d = fma(dz, dz, fma(dx, dx, f(dy * dy)))
                 d2 = min(d, temp[k])
                 temp[k] = d2
                 if d2 > best[tid]:
@@ -169,7 +179,7 @@ def _fps_literal(pts, m):
 
 
 def test_fps_tie_rule_equals_literal_block_reduction():
-    """The vectorised oracle's tie key (bit-reversed k mod B, then k) == the outcome of the literal strided scan +
+    """The oracle's tie key (bit-reversed k mod B, then k) == the outcome of the literal strided scan +
     tree reduction, including exact distance ties, identical points and never-candidate points."""
     rng = np.random.default_rng(4)
     for n, m in ((1, 3), (2, 4), (5, 8), (37, 20), (70, 40), (130, 24)):
