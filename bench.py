@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--no-components", action="store_true", help="skip the per-kernel timings / roofline block")
     ap.add_argument("--no-alt-falloff", action="store_true", help="skip the second resident leg under the other light model")
     ap.add_argument("--sync-gather", action="store_true", help="wait for every step's gather before the next step")
-    ap.add_argument("--cpu-sample-envs", type=int, default=8)
+    ap.add_argument("--cpu-sample-envs", type=int, default=256)   # ~12 s of one host core
     ap.add_argument("--no-overlap", action="store_true", help="point-cloud path on the same stream as the tactile path")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
     ap.add_argument("--one-input-set", action="store_true",
@@ -233,7 +233,7 @@ def run_reference(args):
     except AttributeError:
         cores = os.cpu_count() or 1
     cores = max(cores, 1)
-    n = max(cores * 2, 8)
+    n = max(cores * 8, 32)      # envs per step: ~0.6 s of every core per step
     gym, P, depth, seg = make_inputs(n, 0, n)
     jobs = cpu_jobs(gym, P, depth, seg, n)
     ctx = mp.get_context("fork")
@@ -626,7 +626,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_serial(wl.gym, wl.P, wl.depth_np, wl.seg_np, args.cpu_sample_envs)
+        cpu = cpu_baseline_serial(wl.gym, wl.P, wl.depth_np, wl.seg_np, min(args.cpu_sample_envs, E))
 
     if gather is not None:
         gather.close()
