@@ -193,3 +193,14 @@ def test_fps_tie_rule_equals_literal_block_reduction():
             cases.append(grid.astype(np.float32))                                             # lattice: many equal distances
         for c in cases:
             assert np.array_equal(ofps.furthest_point_sample(c, m), _fps_literal(c, m)), (n, m)
+
+
+def test_fps_oracle_matches_golden_vectors(golden_dir):
+    """tests/golden/fps_golden.npz (tools/make_golden_fps.py: indices from the literal emulation of the published
+    kernel at N = 1, 37, 400, 5184 with duplicate / identical / never-candidate / lattice inputs) == oracle/fps.c."""
+    g = np.load(os.path.join(golden_dir, "fps_golden.npz"))
+    names = sorted(k[:-4] for k in g.files if k.endswith("_idx"))
+    assert len(names) == 12
+    for name in names:
+        want = g[name + "_idx"]
+        assert np.array_equal(ofps.furthest_point_sample(g[name + "_pts"], len(want)), want), name

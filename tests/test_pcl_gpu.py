@@ -205,6 +205,19 @@ def test_fps_standalone(built_lib, n, m):
         assert np.array_equal(idx[b], ofps.furthest_point_sample(pts[b], m)), f"batch {b}"
 
 
+def test_fps_matches_golden_vectors(built_lib, golden_dir):
+    """tests/golden/fps_golden.npz (indices from the literal emulation of the published kernel, tools/make_golden_fps.py):
+    one warp (37), the cooperative CTA (400), the cluster and the one-CTA kernel (5184) all reproduce them bit for bit."""
+    from isaacgyminsertion_b200.pcl_utils import furthest_point_sample
+    g = np.load(os.path.join(golden_dir, "fps_golden.npz"))
+    for name in sorted(k[:-4] for k in g.files if k.endswith("_idx")):
+        want = g[name + "_idx"]
+        d = torch.from_numpy(g[name + "_pts"]).cuda()[None]
+        for flags in (0, 1):      # 1 = IGI_FPS_NO_CLUSTER
+            got = furthest_point_sample(d, len(want), flags=flags).cpu().numpy()[0]
+            assert np.array_equal(got, want), (name, flags)
+
+
 def test_fps_cluster_equals_block_kernel(built_lib):
     """1025..8192 points: the thread-block-cluster kernel and the one-CTA kernel pick the same indices."""
     from isaacgyminsertion_b200 import _lib
