@@ -31,3 +31,31 @@ def test_cpu_tensor_is_rejected(built_lib):
     import torch
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         _lib.dptr(torch.zeros(4), torch.float32, "x")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built .so the loader raises instead of routing anywhere else."""
+    import pytest
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libigi_b200.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_engines_refuse_a_cpu_device(built_lib):
+    import numpy as np
+    import pytest
+    from isaacgyminsertion_b200.allsight_render import BatchedAllSight
+    with pytest.raises(RuntimeError):
+        BatchedAllSight(2, np.zeros(2, dtype=np.int64), device="cpu")
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "isaacgyminsertion_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
