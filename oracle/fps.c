@@ -9,7 +9,7 @@
  * and is compiled by nvcc with its default -fmad=true, which contracts each expression to
  *     mul(y,y) -> fma(x,x,.) -> fma(z,z,.)
  * (checked in this image: `nvcc -ptx` of exactly these two lines emits mul.f32, fma.rn.f32, fma.rn.f32 in that
- * order).  The explicit fmaf() calls below restate that; the file is built with -ffp-contract=off so nothing else
+ * order; tests/test_fps_contraction.py repeats the check).  The explicit fmaf() calls below restate that; the file is built with -ffp-contract=off so nothing else
  * is contracted.  The CUDA kernels use __fmaf_rn / __fmul_rn in the same order, so indices compare bit-for-bit.
  */
 #include <math.h>
