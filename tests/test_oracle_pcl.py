@@ -204,3 +204,20 @@ def test_fps_oracle_matches_golden_vectors(golden_dir):
     for name in names:
         want = g[name + "_idx"]
         assert np.array_equal(ofps.furthest_point_sample(g[name + "_pts"], len(want)), want), name
+
+
+def test_fps_oracle_degenerate_inputs():
+    """Empty task, a single pick, fewer points than picks, and a cloud with no candidate at all (every |p|^2 <= 1e-3):
+    the last one returns index 0 for every pick, like the published kernel whose reduction starts from (best=-1, i=0)."""
+    assert ofps.furthest_point_sample(np.zeros((0, 3), np.float32), 5).tolist() == [0] * 5
+    pts = (np.random.default_rng(0).random((9, 3)) * 0.5 + 0.1).astype(np.float32)
+    assert ofps.furthest_point_sample(pts, 1).tolist() == [0]
+    many = ofps.furthest_point_sample(pts, 30)
+    assert np.array_equal(many, _fps_literal(pts, 30))
+    assert sorted(set(many[:9].tolist())) == list(range(9))          # the first n picks visit every point once
+    assert len(set(many[9:].tolist())) == 1                          # then the arg-max of all-zero distances repeats
+    tiny = (pts * 0.01).astype(np.float32)                           # |p|^2 < 1e-3 everywhere
+    assert ofps.furthest_point_sample(tiny, 6).tolist() == [0] * 6
+    assert _fps_literal(tiny, 6).tolist() == [0] * 6
+    out, idx = ofps.fps_batch([np.zeros((0, 3), np.float32), np.zeros((4, 3), np.float32), pts], 4)
+    assert not out[0].any() and not out[1].any() and out[2].any() and idx[:2].sum() == 0   # `pts.any()` rule
